@@ -1,0 +1,75 @@
+"""ctypes binding of ``lib/libi2vsgg_b200.so`` (the C ABI declared in ``include/i2vsgg_b200.h``).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libi2vsgg_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+IMPL_AUTO, IMPL_GATHER, IMPL_PLANE = 0, 1, 2
+ARGMAX_FLAT, ARGMAX_PLANE = 0, 1
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/i2vsgg_b200.h one to one
+SIGNATURES = {
+    "i2v_last_error": (ctypes.c_char_p, []),
+    "i2v_abi_version": (_i, []),
+    "ROIAlignForwardLaucher": (_i, [_vp, _f, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ROIAlignBackwardLaucher": (_i, [_vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ROIPoolForwardLaucher": (_i, [_vp, _f, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ROIPoolBackwardLaucher": (_i, [_vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "nms_cuda_compute": (None, [_vp, _vp, _vp, _i, _i, _f]),
+    "i2v_roi_align_workspace_bytes": (_sz, [_i, _i]),
+    "i2v_roi_align_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "i2v_roi_align_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "i2v_roi_pool_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "i2v_roi_pool_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "i2v_c_roi_align_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "i2v_c_roi_align_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "i2v_nms_workspace_bytes": (_sz, [_i, _i]),
+    "i2v_nms_sorted": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "i2v_nms_dets_workspace_bytes": (_sz, [_i]),
+    "i2v_nms_dets": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_proposal_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "i2v_proposal_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_proposal_stages": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_pair_build": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "i2v_triplet_topk_workspace_bytes": (_sz, [_i, _i]),
+    "i2v_triplet_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class I2VError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Loads the library (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise I2VError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C i2vsgg_b200/csrc`; i2vsgg_b200 has no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        msg = load().i2v_last_error().decode("utf-8", "replace")
+        raise I2VError(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,122 @@
+// Error reporting, ABI version and the five drop-in launchers that keep the reference's names and argument
+// lists (lib/model/roi_align/src/roi_align_kernel.h:13-27, lib/model/roi_pooling/src/roi_pooling_kernel.h:8-18,
+// lib/model/nms/src/nms_cuda_kernel.h:5-6).  The launchers have no workspace argument, so they keep one grow-only
+// device buffer per (thread, device); everything else in the library takes the caller's workspace.
+#include <limits.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace i2v {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+};
+static thread_local Scratch g_scratch;
+
+// Grow-only scratch for the legacy launchers.  Growing synchronises the device (the old buffer may still be in
+// use by work queued on another stream), which happens a handful of times per process.
+void* legacy_scratch(size_t bytes, size_t* have) {
+    int dev = 0;
+    if (have) *have = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (g_scratch.ptr && g_scratch.device == dev && g_scratch.bytes >= bytes) {
+        if (have) *have = g_scratch.bytes;
+        return g_scratch.ptr;
+    }
+    if (g_scratch.ptr && g_scratch.device == dev) {
+        cudaDeviceSynchronize();
+        cudaFree(g_scratch.ptr);
+    }
+    g_scratch = Scratch{};
+    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 2;
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        set_error("legacy launcher: cudaMalloc(%zu) failed", want);
+        cudaGetLastError();
+        return nullptr;
+    }
+    g_scratch.ptr = p;
+    g_scratch.bytes = want;
+    g_scratch.device = dev;
+    if (have) *have = want;
+    return p;
+}
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" const char* i2v_last_error(void) { return g_error; }
+extern "C" int i2v_abi_version(void) { return 1; }
+
+extern "C" int ROIPoolForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                                     const int height, const int width, const int channels, const int pooled_height,
+                                     const int pooled_width, const float* bottom_rois, float* top_data,
+                                     int* argmax_data, cudaStream_t stream) {
+    // roi_pooling_kernel.h:8-12 does not pass the batch size: accept every frame index whose flat arg-max
+    // (roi_pooling_kernel.cu:85) still fits the int32 output
+    int64_t frame = (int64_t)channels * height * width;
+    int max_batch = (int)(INT32_MAX / (frame > 0 ? frame : 1));
+    if (max_batch < 1) {
+        set_error("ROIPoolForwardLaucher: one frame does not fit the int32 arg-max");
+        return 0;
+    }
+    int rc = i2v_roi_pool_forward(bottom_data, bottom_rois, top_data, argmax_data, max_batch, channels, height, width, num_rois,
+                              pooled_height, pooled_width, spatial_scale, I2V_ARGMAX_FLAT, stream);
+    return rc == I2V_OK ? 1 : 0;
+}
+
+extern "C" int ROIPoolBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
+                                      const int num_rois, const int height, const int width, const int channels,
+                                      const int pooled_height, const int pooled_width, const float* bottom_rois,
+                                      float* bottom_diff, const int* argmax_data, cudaStream_t stream) {
+    int rc = i2v_roi_pool_backward(top_diff, bottom_rois, argmax_data, bottom_diff, batch_size, channels, height, width,
+                                   num_rois, pooled_height, pooled_width, spatial_scale, I2V_ARGMAX_FLAT, stream);
+    return rc == I2V_OK ? 1 : 0;
+}
+
+extern "C" void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_num, int boxes_dim,
+                                 float nms_overlap_thresh) {
+    if (boxes_num < 0 || boxes_dim < 4 || !keep_out || !num_out) {
+        set_error("nms_cuda_compute: bad argument");
+        return;
+    }
+    size_t box_bytes = align_up((size_t)boxes_num * boxes_dim * sizeof(float), 256);
+    size_t need = box_bytes + i2v_nms_workspace_bytes(1, boxes_num);
+    size_t have = 0;
+    char* ws = static_cast<char*>(legacy_scratch(need, &have));
+    if (!ws) return;
+    const float* dev_boxes = boxes_host;
+    cudaPointerAttributes attr;
+    bool on_device = (cudaPointerGetAttributes(&attr, boxes_host) == cudaSuccess) &&
+                     (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (!on_device && boxes_num > 0) {
+        // nms_cuda_kernel.cu:99-101: a blocking host-to-device copy of the box list
+        if (cudaMemcpy(ws, boxes_host, (size_t)boxes_num * boxes_dim * sizeof(float), cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+            set_error("nms_cuda_compute: copying boxes to the device failed");
+            cudaGetLastError();
+            return;
+        }
+        dev_boxes = reinterpret_cast<const float*>(ws);
+    }
+    int rc = i2v_nms_sorted(dev_boxes, 1, boxes_num, boxes_dim, nms_overlap_thresh, 0, keep_out, boxes_num, num_out,
+                            ws + box_bytes, have - box_bytes, 0);
+    if (rc != I2V_OK) return;
+    if (cudaStreamSynchronize(0) != cudaSuccess) {  // synchronous like the reference (nms_cuda_kernel.cu:117-160)
+        set_error("nms_cuda_compute: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+}

@@ -1,0 +1,275 @@
+// SGG pair stage and triplet selection for sm_100a.
+//
+// Reference semantics:
+//   pair enumeration  lib/model/faster_rcnn/faster_rcnn_SGG_emb.py:597-606   (all ordered i != j, i-major)
+//   union boxes       lib/model/faster_rcnn/resnet_SGG_emb.py:240-244 applied per pair at faster_rcnn_SGG_emb.py:649-653
+//   dual masks        lib/model/faster_rcnn/resnet_SGG_emb.py:246-256, stacked at faster_rcnn_SGG_emb.py:654-655
+//   triplet top-100   lib/utils.py:609-626
+//
+// One launch builds everything a frame's pair list needs (indices, union boxes, 32x32 dual masks); one launch
+// selects the top-k triplets of a frame (radix select over the descending-order keys in shared-memory histograms,
+// ordered tie handling, bitonic sort of the winners, record gather).
+#include "common.cuh"
+
+namespace i2v {
+
+// ------------------------------------------------------------------------------------------ pair build
+__device__ __forceinline__ void mask_extent(const float* __restrict__ bb, double rh, double rw, int& x1, int& x2,
+                                            int& y1, int& y2) {
+    // resnet_SGG_emb.py:249-252, evaluated in double like the Python floats
+    x1 = max(0, (int)floor((double)bb[0] * rw));
+    x2 = min(32, (int)ceil((double)bb[2] * rw));
+    y1 = max(0, (int)floor((double)bb[1] * rh));
+    y2 = min(32, (int)ceil((double)bb[3] * rh));
+}
+
+__global__ void __launch_bounds__(256) pair_build_kernel(const float* __restrict__ boxes, int N, float im_h,
+                                                         float im_w, float margin, int64_t* __restrict__ ixs,
+                                                         int64_t* __restrict__ ixo, float* __restrict__ rel_boxes,
+                                                         float* __restrict__ masks) {
+    const int p = blockIdx.x;
+    const int i = p / (N - 1);
+    const int jj = p - i * (N - 1);
+    const int j = jj + (jj >= i ? 1 : 0);
+    const float* s = boxes + (size_t)i * 4;
+    const float* o = boxes + (size_t)j * 4;
+    if (threadIdx.x == 0) {
+        if (ixs) ixs[p] = i;
+        if (ixo) ixo[p] = j;
+        if (rel_boxes) {
+            double m = (double)margin;
+            float* r = rel_boxes + (size_t)p * 5;
+            r[0] = 0.f;
+            r[1] = (float)fmax(0.0, fmin((double)s[0], (double)o[0]) - m);
+            r[2] = (float)fmax(0.0, fmin((double)s[1], (double)o[1]) - m);
+            r[3] = (float)fmin((double)im_w, fmax((double)s[2], (double)o[2]) + m);
+            r[4] = (float)fmin((double)im_h, fmax((double)s[3], (double)o[3]) + m);
+        }
+    }
+    if (!masks) return;
+    const double rh = 32.0 / (double)im_h, rw = 32.0 / (double)im_w;
+    // threads 0-127 paint the subject mask, 128-255 the object mask; 8 cells (two float4) per thread
+    const int which = threadIdx.x >> 7, t = threadIdx.x & 127;
+    int x1, x2, y1, y2;
+    mask_extent(which ? o : s, rh, rw, x1, x2, y1, y2);
+    float4* dst = reinterpret_cast<float4*>(masks + ((size_t)p * 2 + which) * 1024);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int v = t * 2 + q;          // float4 index inside the 32x32 mask
+        int y = v >> 3, xb = (v & 7) * 4;
+        bool row = (y >= y1 && y < y2);
+        float4 m;
+        m.x = (row && xb + 0 >= x1 && xb + 0 < x2) ? 1.f : 0.f;
+        m.y = (row && xb + 1 >= x1 && xb + 1 < x2) ? 1.f : 0.f;
+        m.z = (row && xb + 2 >= x1 && xb + 2 < x2) ? 1.f : 0.f;
+        m.w = (row && xb + 3 >= x1 && xb + 3 < x2) ? 1.f : 0.f;
+        dst[v] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ triplet top-k
+constexpr int kTopThreads = 1024;
+constexpr int kTopMax = 1024;  // largest supported top_k
+
+__device__ __forceinline__ unsigned topk_desc_key(float f) {
+    unsigned u = __float_as_uint(f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~u;
+}
+__device__ __forceinline__ float topk_key_value(unsigned k) {
+    unsigned u = ~k;
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+
+// Single CTA.  keys[] (workspace, P*R uint32) holds the descending-order key of rel*conf_s*conf_o.
+__global__ void __launch_bounds__(kTopThreads) triplet_topk_kernel(
+    const float* __restrict__ rel_score, const float* __restrict__ conf, const int64_t* __restrict__ classes,
+    const float* __restrict__ boxes, const int64_t* __restrict__ ixs, const int64_t* __restrict__ ixo, int P, int R,
+    int top_k, unsigned* __restrict__ keys, float* __restrict__ record_out, int* __restrict__ count_out) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned long long cand[kTopMax];
+    __shared__ unsigned s_prefix, s_need, s_cnt, s_warp[32], s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = P * R;
+    const int K = min(top_k, total);
+
+    // keys: (rel * conf[ixs]) * conf[ixo], each product rounded to fp32 (lib/utils.py:611)
+    for (int i = tid; i < total; i += kTopThreads) {
+        int p = i / R;
+        float v = __fmul_rn(__fmul_rn(rel_score[i], __ldg(conf + ixs[p])), __ldg(conf + ixo[p]));
+        keys[i] = topk_desc_key(v);
+    }
+    if (tid == 0) {
+        s_prefix = 0;
+        s_need = K;
+    }
+    __syncthreads();
+
+    // radix select, most significant digit first (11 + 11 + 10 bits): afterwards s_prefix is the key of the K-th
+    // element and s_need the number of elements equal to it that still belong to the top K
+    const int shifts[3] = {21, 10, 0};
+    const int bits[3] = {11, 11, 10};
+    unsigned known_mask = 0;
+    for (int pass = 0; pass < 3 && K > 0; ++pass) {
+        for (int i = tid; i < 2048; i += kTopThreads) hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        const unsigned dmask = (1u << bits[pass]) - 1u;
+        for (int i = tid; i < total; i += kTopThreads) {
+            unsigned k = keys[i];
+            if ((k & known_mask) == prefix) atomicAdd(&hist[(k >> shifts[pass]) & dmask], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // find the digit where the running count reaches s_need: 64 bins per lane
+            const int per = (1 << bits[pass]) / 32;
+            unsigned sum = 0;
+            for (int q = 0; q < per; ++q) sum += hist[lane * per + q];
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            unsigned need = s_need;
+            unsigned excl = incl - sum;
+            bool mine = (excl < need) && (incl >= need);
+            if (mine) {
+                unsigned run = excl;
+                for (int q = 0; q < per; ++q) {
+                    unsigned c = hist[lane * per + q];
+                    if (run + c >= need) {
+                        s_prefix = prefix | ((unsigned)(lane * per + q) << shifts[pass]);
+                        s_need = need - run;
+                        break;
+                    }
+                    run += c;
+                }
+            }
+        }
+        known_mask |= dmask << shifts[pass];
+        __syncthreads();
+    }
+
+    // collect: everything strictly better than the threshold (any order), then the first s_need ties in index order
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const unsigned thr = s_prefix;
+    const unsigned need_ties = s_need;
+    if (K > 0) {
+        for (int i = tid; i < total; i += kTopThreads) {
+            unsigned k = keys[i];
+            if (k < thr) {
+                unsigned slot = atomicAdd(&s_cnt, 1u);
+                cand[slot] = ((unsigned long long)k << 32) | (unsigned)i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_base = s_cnt;  // == K - need_ties
+        __syncthreads();
+        unsigned taken = 0;
+        for (int i0 = 0; i0 < total && taken < need_ties; i0 += kTopThreads) {
+            int i = i0 + tid;
+            bool tie = (i < total) && (keys[i] == thr);
+            unsigned m = __ballot_sync(0xffffffffu, tie);
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            unsigned before = 0, all = 0;
+            for (int w = 0; w < 32; ++w) {
+                unsigned c = s_warp[w];
+                if (w < warp) before += c;
+                all += c;
+            }
+            unsigned rank = taken + before + __popc(m & ((1u << lane) - 1u));
+            if (tie && rank < need_ties) cand[s_base + rank] = ((unsigned long long)thr << 32) | (unsigned)i;
+            taken += all;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // bitonic sort of the K winners by (key, index) ascending == (score descending, flat index ascending)
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    for (int i = K + tid; i < n2; i += kTopThreads) cand[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < n2 / 2; t += kTopThreads) {
+                int lo = (t / stride) * stride * 2 + (t % stride);
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                unsigned long long a = cand[lo], b = cand[hi];
+                if ((a > b) == up) {
+                    cand[lo] = b;
+                    cand[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // records: (conf, cls_s, rel, cls_o, sub box x4, obj box x4, pair idx); zero rows past K
+    for (int t = tid; t < top_k; t += kTopThreads) {
+        float* rec = record_out + (size_t)t * 13;
+        if (t < K) {
+            unsigned long long e = cand[t];
+            unsigned flat = (unsigned)(e & 0xffffffffu);
+            int p = flat / R, r = flat - p * R;
+            int64_t si = ixs[p], oi = ixo[p];
+            rec[0] = topk_key_value((unsigned)(e >> 32));
+            rec[1] = (float)classes[si];
+            rec[2] = (float)r;
+            rec[3] = (float)classes[oi];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rec[4 + q] = boxes[si * 4 + q];
+                rec[8 + q] = boxes[oi * 4 + q];
+            }
+            rec[12] = (float)p;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 13; ++q) rec[q] = 0.f;
+        }
+    }
+    if (tid == 0 && count_out) *count_out = K;
+}
+
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" int i2v_pair_build(const float* boxes, int num_boxes, float im_h, float im_w, float margin, int64_t* ixs,
+                              int64_t* ixo, float* rel_boxes, float* masks, cudaStream_t stream) {
+    I2V_REQUIRE(num_boxes >= 0, "pair_build: bad size");
+    if (num_boxes < 2) return I2V_OK;  // faster_rcnn_SGG_emb.py:590-595: no pairs
+    I2V_REQUIRE(boxes, "pair_build: null boxes");
+    I2V_REQUIRE((int64_t)num_boxes * (num_boxes - 1) <= INT32_MAX, "pair_build: too many pairs");
+    I2V_REQUIRE(!masks || ((uintptr_t)masks & 15) == 0, "pair_build: masks must be 16-byte aligned");
+    int P = num_boxes * (num_boxes - 1);
+    pair_build_kernel<<<P, 256, 0, stream>>>(boxes, num_boxes, im_h, im_w, margin, ixs, ixo, rel_boxes, masks);
+    return check_launch("pair_build_kernel");
+}
+
+extern "C" size_t i2v_triplet_topk_workspace_bytes(int num_pairs, int num_rel) {
+    if (num_pairs < 0 || num_rel < 0) return 0;
+    return align_up((size_t)num_pairs * num_rel * sizeof(unsigned), 256);
+}
+
+extern "C" int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
+                                const int64_t* ixs, const int64_t* ixo, int num_pairs, int num_rel, int top_k,
+                                float* record_out, int* count_out, void* workspace, size_t workspace_bytes,
+                                cudaStream_t stream) {
+    I2V_REQUIRE(num_pairs >= 0 && num_rel >= 0 && top_k >= 1 && top_k <= kTopMax, "triplet_topk: bad size (top_k <= %d)", kTopMax);
+    I2V_REQUIRE((int64_t)num_pairs * num_rel <= INT32_MAX, "triplet_topk: too many scores");
+    I2V_REQUIRE(record_out, "triplet_topk: null record_out");
+    size_t need = i2v_triplet_topk_workspace_bytes(num_pairs, num_rel);
+    if (need > 0) {
+        I2V_REQUIRE(rel_score && conf && classes && boxes && ixs && ixo, "triplet_topk: null pointer");
+        if (!workspace || workspace_bytes < need) {
+            set_error("triplet_topk: workspace %zu < %zu bytes", workspace_bytes, need);
+            return I2V_ERR_WORKSPACE;
+        }
+    }
+    triplet_topk_kernel<<<1, kTopThreads, 0, stream>>>(rel_score, conf, classes, boxes, ixs, ixo, num_pairs, num_rel,
+                                                       top_k, static_cast<unsigned*>(workspace), record_out, count_out);
+    return check_launch("triplet_topk_kernel");
+}

@@ -1,0 +1,247 @@
+"""Tensor-level entry points over the C ABI: every function takes CUDA tensors, runs on torch's current
+stream and returns new tensors.  torch is used for device memory and streams only; all arithmetic happens in
+``libi2vsgg_b200.so``.  CPU tensors are rejected -- there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ARGMAX_FLAT, ARGMAX_PLANE, IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, POOL_AVG, POOL_MAX, POOL_NONE,
+                   check, load)
+
+_POOLS = {"none": POOL_NONE, "avg": POOL_AVG, "max": POOL_MAX, POOL_NONE: POOL_NONE, POOL_AVG: POOL_AVG,
+          POOL_MAX: POOL_MAX}
+_IMPLS = {"auto": IMPL_AUTO, "gather": IMPL_GATHER, "plane": IMPL_PLANE, IMPL_AUTO: IMPL_AUTO,
+          IMPL_GATHER: IMPL_GATHER, IMPL_PLANE: IMPL_PLANE}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.I2VError(f"{what}: expected a CUDA tensor (i2vsgg_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _rois5(rois: torch.Tensor) -> torch.Tensor:
+    rois = _f32(rois, "rois")
+    if rois.dim() != 2 or rois.size(1) != 5:
+        # roi_align_cuda.c:19-22 / roi_pooling_cuda.c:20-23 return 0 here; a drop-in that silently did nothing
+        # would hide the bug, so this raises instead
+        raise _lib.I2VError(f"rois must be [N,5], got {tuple(rois.shape)}")
+    return rois
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------- lattice RoIAlign
+def roi_align_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float, pool="none", impl="auto"):
+    """RoIAlign / RoIAlignAvg / RoIAlignMax forward (modules/roi_align.py:6-42) -> [N,C,pooled_h,pooled_w]."""
+    features, rois = _f32(features, "features"), _rois5(rois)
+    B, C, H, W = features.shape
+    N = rois.size(0)
+    out = torch.empty((N, C, pooled_h, pooled_w), dtype=torch.float32, device=features.device)
+    lib = load()
+    with torch.cuda.device(features.device):
+        nb = lib.i2v_roi_align_workspace_bytes(B, N)
+        ws = _workspace(nb, features.device)
+        check(lib.i2v_roi_align_forward(_p(features), _p(rois), _p(out), B, C, H, W, N, pooled_h, pooled_w,
+                                        float(spatial_scale), _POOLS[pool], _IMPLS[impl], _p(ws), ws.numel(),
+                                        _stream()), "i2v_roi_align_forward")
+    return out
+
+
+def roi_align_backward(grad_out, features, rois, feat_shape, pooled_h: int, pooled_w: int, spatial_scale: float,
+                       pool="none", impl="auto"):
+    """Gradient of the above w.r.t. the features -> [B,C,H,W].  `features` is only read for pool='max'."""
+    grad_out, rois = _f32(grad_out, "grad_out"), _rois5(rois)
+    B, C, H, W = feat_shape
+    N = rois.size(0)
+    if _POOLS[pool] == POOL_MAX:
+        features = _f32(features, "features")
+    else:
+        features = None
+    grad_in = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    lib = load()
+    with torch.cuda.device(grad_out.device):
+        ws = _workspace(lib.i2v_roi_align_workspace_bytes(B, N), grad_out.device)
+        check(lib.i2v_roi_align_backward(_p(grad_out), _p(features), _p(rois), _p(grad_in), B, C, H, W, N, pooled_h,
+                                         pooled_w, float(spatial_scale), _POOLS[pool], _IMPLS[impl], _p(ws),
+                                         ws.numel(), _stream()), "i2v_roi_align_backward")
+    return grad_in
+
+
+# --------------------------------------------------------------------------------------- RoIPool
+def roi_pool_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float, argmax_mode=ARGMAX_FLAT):
+    features, rois = _f32(features, "features"), _rois5(rois)
+    B, C, H, W = features.shape
+    N = rois.size(0)
+    out = torch.empty((N, C, pooled_h, pooled_w), dtype=torch.float32, device=features.device)
+    argmax = torch.empty((N, C, pooled_h, pooled_w), dtype=torch.int32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(load().i2v_roi_pool_forward(_p(features), _p(rois), _p(out), _p(argmax), B, C, H, W, N, pooled_h,
+                                          pooled_w, float(spatial_scale), argmax_mode, _stream()),
+              "i2v_roi_pool_forward")
+    return out, argmax
+
+
+def roi_pool_backward(grad_out, rois, argmax, feat_shape, pooled_h: int, pooled_w: int, spatial_scale: float,
+                      argmax_mode=ARGMAX_FLAT):
+    grad_out, rois = _f32(grad_out, "grad_out"), _rois5(rois)
+    argmax = argmax.contiguous()
+    assert argmax.dtype == torch.int32 and argmax.is_cuda
+    B, C, H, W = feat_shape
+    grad_in = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(load().i2v_roi_pool_backward(_p(grad_out), _p(rois), _p(argmax), _p(grad_in), B, C, H, W, rois.size(0),
+                                           pooled_h, pooled_w, float(spatial_scale), argmax_mode, _stream()),
+              "i2v_roi_pool_backward")
+    return grad_in
+
+
+# --------------------------------------------------------------------------------------- model._C RoIAlign
+def c_roi_align_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float, sampling_ratio: int):
+    features, rois = _f32(features, "features"), _rois5(rois)
+    B, C, H, W = features.shape
+    out = torch.empty((rois.size(0), C, pooled_h, pooled_w), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(load().i2v_c_roi_align_forward(_p(features), _p(rois), _p(out), B, C, H, W, rois.size(0), pooled_h,
+                                             pooled_w, float(spatial_scale), int(sampling_ratio), _stream()),
+              "i2v_c_roi_align_forward")
+    return out
+
+
+def c_roi_align_backward(grad_out, rois, feat_shape, pooled_h: int, pooled_w: int, spatial_scale: float,
+                         sampling_ratio: int):
+    grad_out, rois = _f32(grad_out, "grad_out"), _rois5(rois)
+    B, C, H, W = feat_shape
+    grad_in = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(load().i2v_c_roi_align_backward(_p(grad_out), _p(rois), _p(grad_in), B, C, H, W, rois.size(0), pooled_h,
+                                              pooled_w, float(spatial_scale), int(sampling_ratio), _stream()),
+              "i2v_c_roi_align_backward")
+    return grad_in
+
+
+# --------------------------------------------------------------------------------------- NMS
+def nms_sorted(boxes, thresh: float, max_keep: int = 0):
+    """boxes [N,>=4] or [B,N,>=4], rows already in descending score order -> (keep [.., K] int32, counts)."""
+    boxes = _f32(boxes, "boxes")
+    single = boxes.dim() == 2
+    if single:
+        boxes = boxes.unsqueeze(0)
+    B, N, S = boxes.shape
+    kcap = min(N, max_keep) if max_keep > 0 else N
+    keep = torch.zeros((B, max(kcap, 1)), dtype=torch.int32, device=boxes.device)
+    num = torch.zeros((B,), dtype=torch.int32, device=boxes.device)
+    lib = load()
+    with torch.cuda.device(boxes.device):
+        ws = _workspace(lib.i2v_nms_workspace_bytes(B, N), boxes.device)
+        check(lib.i2v_nms_sorted(_p(boxes), B, N, S, float(thresh), int(max_keep), _p(keep), keep.size(1), _p(num),
+                                 _p(ws), ws.numel(), _stream()), "i2v_nms_sorted")
+    if single:
+        return keep[0, : int(num[0].item())], num
+    return keep, num
+
+
+def nms_dets(dets, thresh: float):
+    """nms_wrapper.nms(): dets [N,5] (x1,y1,x2,y2,score) in any order -> kept original row indices, int32."""
+    dets = _f32(dets, "dets")
+    if dets.dim() != 2 or dets.size(1) != 5:
+        raise _lib.I2VError(f"dets must be [N,5], got {tuple(dets.shape)}")
+    N = dets.size(0)
+    keep = torch.empty((max(N, 1),), dtype=torch.int32, device=dets.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=dets.device)
+    lib = load()
+    with torch.cuda.device(dets.device):
+        ws = _workspace(lib.i2v_nms_dets_workspace_bytes(N), dets.device)
+        check(lib.i2v_nms_dets(_p(dets), N, float(thresh), _p(keep), _p(num), _p(ws), ws.numel(), _stream()),
+              "i2v_nms_dets")
+    return keep[: int(num.item())]
+
+
+# --------------------------------------------------------------------------------------- proposal layer
+def proposal_forward(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: int, pre_nms_top_n: int,
+                     post_nms_top_n: int, nms_thresh: float, return_counts: bool = False):
+    """_ProposalLayer.forward (proposal_layer.py:49-163) -> rois [B, post_nms_top_n, 5]."""
+    cls_prob, bbox_pred = _f32(cls_prob, "cls_prob"), _f32(bbox_pred, "bbox_pred")
+    im_info, base_anchors = _f32(im_info, "im_info"), _f32(base_anchors, "base_anchors")
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    if bbox_pred.shape != (B, 4 * A, H, W) or base_anchors.shape != (A, 4) or im_info.shape != (B, 3):
+        raise _lib.I2VError("proposal_forward: inconsistent shapes")
+    out = torch.empty((B, post_nms_top_n, 5), dtype=torch.float32, device=cls_prob.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=cls_prob.device)
+    lib = load()
+    with torch.cuda.device(cls_prob.device):
+        ws = _workspace(lib.i2v_proposal_workspace_bytes(B, A, H, W, pre_nms_top_n), cls_prob.device)
+        check(lib.i2v_proposal_forward(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(base_anchors), B, A, H, W,
+                                       int(feat_stride), int(pre_nms_top_n), int(post_nms_top_n), float(nms_thresh),
+                                       _p(out), _p(counts), _p(ws), ws.numel(), _stream()), "i2v_proposal_forward")
+    return (out, counts) if return_counts else out
+
+
+def proposal_stages(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: int, want_order: bool = True):
+    """Decoded+clipped boxes [B,KA,4], scores [B,KA] and the descending-score order [B,KA] (tests)."""
+    cls_prob, bbox_pred = _f32(cls_prob, "cls_prob"), _f32(bbox_pred, "bbox_pred")
+    im_info, base_anchors = _f32(im_info, "im_info"), _f32(base_anchors, "base_anchors")
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    KA = A * H * W
+    dev = cls_prob.device
+    boxes = torch.empty((B, KA, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, KA), dtype=torch.float32, device=dev)
+    order = torch.empty((B, KA), dtype=torch.int32, device=dev) if want_order else None
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.i2v_proposal_workspace_bytes(B, A, H, W, 0), dev)
+        check(lib.i2v_proposal_stages(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(base_anchors), B, A, H, W,
+                                      int(feat_stride), _p(boxes), _p(scores), _p(order), _p(ws), ws.numel(),
+                                      _stream()), "i2v_proposal_stages")
+    return boxes, scores, order
+
+
+# --------------------------------------------------------------------------------------- SGG pair stage
+def pair_build(boxes, im_h: float, im_w: float, margin: float = 10.0, want_masks: bool = True):
+    """boxes [N,4] -> (ixs [P], ixo [P] int64, rel_boxes [P,5], masks [P,2,32,32] or None), P = N(N-1)."""
+    boxes = _f32(boxes, "boxes")
+    N = boxes.size(0)
+    P = N * (N - 1) if N > 1 else 0
+    dev = boxes.device
+    ixs = torch.empty((P,), dtype=torch.int64, device=dev)
+    ixo = torch.empty((P,), dtype=torch.int64, device=dev)
+    rel = torch.empty((P, 5), dtype=torch.float32, device=dev)
+    masks = torch.empty((P, 2, 32, 32), dtype=torch.float32, device=dev) if want_masks else None
+    with torch.cuda.device(dev):
+        check(load().i2v_pair_build(_p(boxes), N, float(im_h), float(im_w), float(margin), _p(ixs), _p(ixo), _p(rel),
+                                    _p(masks), _stream()), "i2v_pair_build")
+    return ixs, ixo, rel, masks
+
+
+def triplet_topk(rel_score, conf, classes, boxes, ixs, ixo, top_k: int = 100):
+    """lib/utils.py:609-626 on the device -> (records [top_k,13] fp32, count int32[1])."""
+    rel_score, conf, boxes = _f32(rel_score, "rel_score"), _f32(conf, "conf"), _f32(boxes, "boxes")
+    classes, ixs, ixo = classes.long().contiguous(), ixs.long().contiguous(), ixo.long().contiguous()
+    P, R = rel_score.shape
+    dev = rel_score.device
+    rec = torch.empty((top_k, 13), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.i2v_triplet_topk_workspace_bytes(P, R), dev)
+        check(lib.i2v_triplet_topk(_p(rel_score), _p(conf), _p(classes), _p(boxes), _p(ixs), _p(ixo), P, R,
+                                   int(top_k), _p(rec), _p(cnt), _p(ws), ws.numel(), _stream()), "i2v_triplet_topk")
+    return rec, cnt

@@ -1,0 +1,160 @@
+"""Seeded synthetic inputs for the region-level hot path.
+
+Shapes follow a 600x1000 VidVRD frame through ResNet-101 conv4: feature map
+``[B,1024,38,63]``, A=9 anchors, K*A = 21546 candidates per frame.  Everything is built
+with numpy on the host from an integer seed so the CPU oracle and the CUDA path see the
+same bits; callers move the arrays to the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+IM_H, IM_W = 600.0, 1000.0
+FEAT_H, FEAT_W, FEAT_C = 38, 63, 1024
+NUM_ANCHORS = 9
+FEAT_STRIDE = 16
+
+# generate_anchors.py:12-37 golden table minus 1 (scales 8,16,32 x ratios .5,1,2, base 16)
+BASE_ANCHORS = np.array(
+    [[-84., -40., 99., 55.], [-176., -88., 191., 103.], [-360., -184., 375., 199.],
+     [-56., -56., 71., 71.], [-120., -120., 135., 135.], [-248., -248., 263., 263.],
+     [-36., -80., 51., 95.], [-80., -168., 95., 183.], [-168., -344., 183., 359.]], dtype=np.float32)
+
+
+def feature_map(seed: int, batch: int = 1, channels: int = FEAT_C, h: int = FEAT_H, w: int = FEAT_W) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((batch, channels, h, w), dtype=np.float32)
+
+
+def im_info(batch: int = 1) -> np.ndarray:
+    return np.tile(np.array([[IM_H, IM_W, 1.0]], np.float32), (batch, 1))
+
+
+def rois(seed: int, num: int, batch: int = 1, edge_frac: float = 0.05, degenerate: int = 2,
+         sort_by_batch: bool = False) -> np.ndarray:
+    """Stand-alone RoIs [num,5] = (b, x1, y1, x2, y2) in image pixels.
+
+    ~`edge_frac` of them run past the right/bottom image edge (exercises the lattice op's
+    `h >= H -> 0` rule) and `degenerate` of them have x2 < x1 or y2 < y1."""
+    rng = np.random.default_rng(seed)
+    x1 = rng.uniform(0, 900, num)
+    y1 = rng.uniform(0, 500, num)
+    bw = rng.uniform(16, 400, num)
+    bh = rng.uniform(16, 400, num)
+    x2 = np.minimum(x1 + bw, IM_W - 1)
+    y2 = np.minimum(y1 + bh, IM_H - 1)
+    past = rng.random(num) < edge_frac
+    x2 = np.where(past, x1 + bw + 60.0, x2)
+    y2 = np.where(past, y1 + bh + 60.0, y2)
+    out = np.stack([rng.integers(0, batch, num).astype(np.float64), x1, y1, x2, y2], 1).astype(np.float32)
+    for k in range(min(degenerate, num)):
+        j = int(rng.integers(0, num))
+        if k % 2 == 0:
+            out[j, 3] = out[j, 1] - 40.0
+        else:
+            out[j, 4] = out[j, 2] - 25.0
+    if sort_by_batch:
+        out = out[np.argsort(out[:, 0], kind="stable")]
+    return np.ascontiguousarray(out)
+
+
+def _anchors(h: int = FEAT_H, w: int = FEAT_W) -> np.ndarray:
+    sx, sy = np.meshgrid(np.arange(w) * FEAT_STRIDE, np.arange(h) * FEAT_STRIDE)
+    shifts = np.stack([sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel()], 1).astype(np.float32)
+    return (BASE_ANCHORS[None, :, :] + shifts[:, None, :]).reshape(-1, 4)
+
+
+def _iou_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    aw = a[:, 2] - a[:, 0] + 1
+    ah = a[:, 3] - a[:, 1] + 1
+    bw = b[:, 2] - b[:, 0] + 1
+    bh = b[:, 3] - b[:, 1] + 1
+    iw = np.clip(np.minimum(a[:, None, 2], b[None, :, 2]) - np.maximum(a[:, None, 0], b[None, :, 0]) + 1, 0, None)
+    ih = np.clip(np.minimum(a[:, None, 3], b[None, :, 3]) - np.maximum(a[:, None, 1], b[None, :, 1]) + 1, 0, None)
+    inter = iw * ih
+    return inter / ((aw * ah)[:, None] + (bw * bh)[None, :] - inter)
+
+
+def rpn_outputs(seed: int, batch: int = 1, h: int = FEAT_H, w: int = FEAT_W, clusters: int = 40):
+    """(cls_prob [B,2A,h,w], bbox_pred [B,4A,h,w]) with unique fg scores per frame.
+
+    fg scores are a permutation of linspace(0,1,K*A) (unique -> deterministic sort and NMS);
+    `clusters` random ground-truth boxes per frame attract every anchor with IoU > 0.5: those anchors
+    get the highest scores and deltas that regress onto the box (+ jitter), so NMS really suppresses
+    the bulk of the candidates, as with a trained RPN."""
+    A = NUM_ANCHORS
+    KA = h * w * A
+    anchors = _anchors(h, w).astype(np.float64)
+    aw = anchors[:, 2] - anchors[:, 0] + 1
+    ah = anchors[:, 3] - anchors[:, 1] + 1
+    acx = anchors[:, 0] + 0.5 * aw
+    acy = anchors[:, 1] + 0.5 * ah
+    cls = np.empty((batch, 2 * A, h, w), np.float32)
+    reg = np.empty((batch, 4 * A, h, w), np.float32)
+    levels = np.linspace(0.0, 1.0, KA, dtype=np.float64).astype(np.float32)
+    for b in range(batch):
+        rng = np.random.default_rng((seed, b))
+        d = np.empty((KA, 4), np.float64)
+        d[:, :2] = rng.normal(0, 0.2, (KA, 2))
+        d[:, 2:] = rng.normal(0, 0.3, (KA, 2))
+        gw = rng.uniform(60, 420, clusters)
+        gh = rng.uniform(60, 420, clusters)
+        gx = rng.uniform(0, IM_W - 1 - gw)
+        gy = rng.uniform(0, IM_H - 1 - gh)
+        gt = np.stack([gx, gy, gx + gw, gy + gh], 1)
+        iou = _iou_matrix(anchors, gt)
+        best = iou.argmax(1)
+        hit = iou[np.arange(KA), best] > 0.5
+        g = gt[best[hit]]
+        gww = g[:, 2] - g[:, 0] + 1
+        ghh = g[:, 3] - g[:, 1] + 1
+        tgt = np.stack([(g[:, 0] + 0.5 * gww - acx[hit]) / aw[hit], (g[:, 1] + 0.5 * ghh - acy[hit]) / ah[hit],
+                        np.log(gww / aw[hit]), np.log(ghh / ah[hit])], 1)
+        d[hit] = tgt + rng.normal(0, 0.05, tgt.shape)
+        nh = int(hit.sum())
+        rank = np.empty(KA, np.int64)
+        rank[np.flatnonzero(hit)] = KA - 1 - rng.permutation(nh)        # top levels
+        rank[np.flatnonzero(~hit)] = rng.permutation(KA - nh)
+        fg = levels[rank]
+        # anchor-major [K, A] -> NCHW channel blocks (proposal_layer.py:100-105 inverts this)
+        cls[b, A:] = fg.reshape(h, w, A).transpose(2, 0, 1)
+        cls[b, :A] = 1.0 - cls[b, A:]
+        reg[b] = d.astype(np.float32).reshape(h, w, A * 4).transpose(2, 0, 1)
+    return cls, reg
+
+
+def nms_dets(seed: int, n: int) -> np.ndarray:
+    """[n,5] dets (x1,y1,x2,y2,score) in random order: boxes clustered like RPN output, unique scores."""
+    rng = np.random.default_rng(seed)
+    m = max(4, n // 25)
+    cx, cy = rng.uniform(50, 950, m), rng.uniform(50, 550, m)
+    w, h = rng.uniform(30, 300, m), rng.uniform(30, 300, m)
+    which = rng.integers(0, m, n)
+    jit = rng.normal(0, 0.12, (n, 4))
+    bw, bh = w[which] * np.exp(jit[:, 2]), h[which] * np.exp(jit[:, 3])
+    bx, by = cx[which] + jit[:, 0] * w[which], cy[which] + jit[:, 1] * h[which]
+    boxes = np.stack([bx - bw / 2, by - bh / 2, bx + bw / 2, by + bh / 2], 1)
+    boxes[:, 0::2] = np.clip(boxes[:, 0::2], 0, 999)
+    boxes[:, 1::2] = np.clip(boxes[:, 1::2], 0, 599)
+    scores = rng.permutation(np.linspace(0.01, 0.99, n))
+    return np.concatenate([boxes, scores[:, None]], 1).astype(np.float32)
+
+
+def detections(seed: int, num: int = 64, num_classes: int = 35):
+    """Config 3: `num` detections of one frame -> (boxes [num,4] fp32, classes [num] int, conf [num] fp32)."""
+    rng = np.random.default_rng(seed)
+    r = rois(seed, num, batch=1, edge_frac=0.0, degenerate=0)[:, 1:]
+    classes = rng.integers(1, num_classes + 1, num).astype(np.int64)
+    conf = rng.uniform(0.05, 1.0, num).astype(np.float32)
+    return np.ascontiguousarray(r), classes, conf
+
+
+def clip_detections(seed: int, frames: int, num: int = 64, sigma: float = 4.0):
+    """Config 5: a clip whose detections drift by a random walk (sigma px) from frame to frame."""
+    rng = np.random.default_rng(seed)
+    boxes0, classes, conf = detections(seed, num)
+    steps = rng.normal(0, sigma, (frames, num, 2)).astype(np.float32).cumsum(0)
+    boxes = np.repeat(boxes0[None], frames, 0)
+    boxes[:, :, 0::2] = np.clip(boxes[:, :, 0::2] + steps[:, :, 0:1], 0, IM_W - 1)
+    boxes[:, :, 1::2] = np.clip(boxes[:, :, 1::2] + steps[:, :, 1:2], 0, IM_H - 1)
+    return boxes, classes, conf

@@ -1,0 +1,163 @@
+/*
+ * i2vsgg_b200.h -- C ABI of libi2vsgg_b200.so, the sm_100a implementation of the I2VSGG
+ * region-level hot path (RPN proposal decode + NMS, RoIAlign / RoIPool forward+backward,
+ * SGG pair enumeration + union boxes + dual masks, triplet top-k, embedding projection).
+ *
+ * Everything is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t, allocates
+ * nothing behind the caller's back (the i2v_* entry points take a caller-provided workspace;
+ * only the five legacy-signature launchers keep a small grow-only cache because their
+ * signatures have no workspace argument) and never calls exit().
+ *
+ * All paths below are relative to the reference tree (/root/reference).
+ */
+#ifndef I2VSGG_B200_H
+#define I2VSGG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if !defined(__DRIVER_TYPES_H__) && !defined(__CUDA_RUNTIME_H__)
+typedef struct CUstream_st* cudaStream_t; /* same opaque type the CUDA runtime declares */
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status ------------------------------------------------------------------------------- */
+#define I2V_OK 0
+#define I2V_ERR_INVALID 1     /* bad argument (shape, null pointer, unsupported size)            */
+#define I2V_ERR_CUDA 2        /* a CUDA call or launch failed; see i2v_last_error()              */
+#define I2V_ERR_WORKSPACE 3   /* workspace smaller than the matching *_workspace_bytes() result  */
+#define I2V_ERR_UNSUPPORTED 4 /* requested implementation cannot handle this shape               */
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* i2v_last_error(void);
+/* ABI version of this library (bumped when a signature changes). */
+int i2v_abi_version(void);
+
+/* ---- 1. Drop-in launchers: same names, argument order and meaning as the reference --------- */
+/* Replaces lib/model/roi_align/src/roi_align_kernel.h:13-17 (impl. roi_align_kernel.cu:73-91).
+ * Returns 1 on success like the reference; 0 (instead of exit(-1), roi_align_kernel.cu:84-88) on error.
+ * top_data need not be pre-zeroed. */
+int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                           const int height, const int width, const int channels, const int aligned_height,
+                           const int aligned_width, const float* bottom_rois, float* top_data,
+                           cudaStream_t stream);
+/* Replaces roi_align_kernel.h:24-27 (impl. roi_align_kernel.cu:145-162).  Like the reference it
+ * ACCUMULATES into bottom_diff, which the caller zeroes first (functions/roi_align.py:42-43). */
+int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
+                            const int num_rois, const int height, const int width, const int channels,
+                            const int aligned_height, const int aligned_width, const float* bottom_rois,
+                            float* bottom_diff, cudaStream_t stream);
+/* Replaces lib/model/roi_pooling/src/roi_pooling_kernel.h:8-12 (impl. roi_pooling_kernel.cu:95-125).
+ * argmax_data may be NULL (roi_pooling_kernel.cu:89-90). */
+int ROIPoolForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                          const int height, const int width, const int channels, const int pooled_height,
+                          const int pooled_width, const float* bottom_rois, float* top_data, int* argmax_data,
+                          cudaStream_t stream);
+/* Replaces roi_pooling_kernel.h:15-18 (impl. roi_pooling_kernel.cu:205-234): overwrites bottom_diff. */
+int ROIPoolBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
+                           const int num_rois, const int height, const int width, const int channels,
+                           const int pooled_height, const int pooled_width, const float* bottom_rois,
+                           float* bottom_diff, const int* argmax_data, cudaStream_t stream);
+/* Replaces lib/model/nms/src/nms_cuda_kernel.h:5-6 (impl. nms_cuda_kernel.cu:87-161).
+ * boxes_host: boxes_num x boxes_dim floats (x1,y1,x2,y2[,score]) in descending score order, host OR
+ * device memory; keep_out / num_out are DEVICE pointers (nms_cuda_kernel.cu:147,154).  Synchronous on
+ * the default stream like the reference, but the greedy scan runs on the device. */
+void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_num, int boxes_dim,
+                      float nms_overlap_thresh);
+
+/* ---- 2. Lattice RoIAlign with the 2x2/stride-1 pool of RoIAlignAvg / RoIAlignMax fused ----- */
+#define I2V_POOL_NONE 0 /* RoIAlign     (modules/roi_align.py:6-16):  lattice = pooled_h x pooled_w       */
+#define I2V_POOL_AVG 1  /* RoIAlignAvg  (modules/roi_align.py:18-29): lattice (ph+1)x(pw+1), avg_pool 2/1 */
+#define I2V_POOL_MAX 2  /* RoIAlignMax  (modules/roi_align.py:31-42): lattice (ph+1)x(pw+1), max_pool 2/1 */
+
+#define I2V_IMPL_AUTO 0    /* plane-resident kernel when the shape allows it, else the gather kernel */
+#define I2V_IMPL_GATHER 1  /* one thread per output element, L1/L2 gathers (any shape)                */
+#define I2V_IMPL_PLANE 2   /* frame plane staged in shared memory; I2V_ERR_UNSUPPORTED if it cannot    */
+
+size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
+/* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.
+ * Semantics: functions/roi_align.py:15-35 + roi_align_kernel.cu:15-70 (+ the module's pool).
+ * RoIs whose batch index is outside [0,B) produce zeros. */
+int i2v_roi_align_forward(const float* features, const float* rois, float* out, int batch, int channels,
+                          int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                          int pool_mode, int impl, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* grad_out [N,C,ph,pw] -> grad_in [B,C,H,W], fully OVERWRITTEN (no pre-zeroing needed).
+ * Semantics: functions/roi_align.py:37-51 + roi_align_kernel.cu:94-143 behind the pool's backward.
+ * `features` is read only for I2V_POOL_MAX (arg-max routing) and may be NULL otherwise. */
+int i2v_roi_align_backward(const float* grad_out, const float* features, const float* rois, float* grad_in,
+                           int batch, int channels, int height, int width, int num_rois, int pooled_h,
+                           int pooled_w, float spatial_scale, int pool_mode, int impl, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- 3. RoIPool ---------------------------------------------------------------------------- */
+#define I2V_ARGMAX_FLAT 0  /* cffi op: index into the whole [B,C,H,W] tensor (roi_pooling_kernel.cu:85) */
+#define I2V_ARGMAX_PLANE 1 /* model._C op: h*W+w within the (b,c) plane (roi_layers/roi_pool.py:17-19)  */
+int i2v_roi_pool_forward(const float* features, const float* rois, float* out, int* argmax, int batch,
+                         int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                         float spatial_scale, int argmax_mode, cudaStream_t stream);
+/* grad_in [B,C,H,W] is overwritten.  Scatter of grad_out to the recorded arg-max cells. */
+int i2v_roi_pool_backward(const float* grad_out, const float* rois, const int* argmax, float* grad_in, int batch,
+                          int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                          float spatial_scale, int argmax_mode, cudaStream_t stream);
+
+/* ---- 4. The RoIAlign behind model._C (roi_layers/roi_align.py:20,31-42; Mask R-CNN, aligned=False) */
+int i2v_c_roi_align_forward(const float* features, const float* rois, float* out, int batch, int channels,
+                            int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                            int sampling_ratio, cudaStream_t stream);
+int i2v_c_roi_align_backward(const float* grad_out, const float* rois, float* grad_in, int batch, int channels,
+                             int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                             int sampling_ratio, cudaStream_t stream);
+
+/* ---- 5. NMS (nms_wrapper.py:13-21 -> nms_cpu.py:6-34; bit-exact keep lists) ------------------ */
+size_t i2v_nms_workspace_bytes(int batch, int num_boxes);
+/* `batch` independent sets of `num_boxes` rows (row stride `box_stride` floats, x1,y1,x2,y2 first), each
+ * already in descending score order.  keep_out [batch, keep_stride] int32 row indices in keep order,
+ * num_out [batch].  max_keep > 0 stops after that many survivors (proposal_layer.py:153-154). */
+int i2v_nms_sorted(const float* boxes, int batch, int num_boxes, int box_stride, float thresh, int max_keep,
+                   int* keep_out, int keep_stride, int* num_out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+/* dets [N,5] (x1,y1,x2,y2,score) in ANY order: sorts by score descending (ties: lower index first), runs the
+ * greedy scan and returns ORIGINAL row indices, i.e. what nms_wrapper.nms() returns. */
+size_t i2v_nms_dets_workspace_bytes(int num_boxes);
+int i2v_nms_dets(const float* dets, int num_boxes, float thresh, int* keep_out, int* num_out, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- 6. Proposal layer (proposal_layer.py:49-163 + bbox_transform.py:77-103,125-133) -------- */
+size_t i2v_proposal_workspace_bytes(int batch, int num_anchors, int height, int width, int pre_nms_top_n);
+/* cls_prob [B,2A,H,W], bbox_pred [B,4A,H,W], im_info [B,3]=(h,w,scale), base_anchors [A,4] (device).
+ * out_rois [B,post_nms_top_n,5] = (b,x1,y1,x2,y2), zero padded; out_counts [B] (may be NULL). */
+int i2v_proposal_forward(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                         const float* base_anchors, int batch, int num_anchors, int height, int width,
+                         int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                         float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+/* Stage outputs for tests: decoded+clipped boxes [B,KA,4], scores [B,KA] in anchor-major order, and (after
+ * the sort) order [B,KA] int32 = candidate indices by descending score.  Any of the three may be NULL. */
+int i2v_proposal_stages(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                        const float* base_anchors, int batch, int num_anchors, int height, int width,
+                        int feat_stride, float* boxes, float* scores, int* order, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- 7. SGG pair stage (faster_rcnn_SGG_emb.py:597-606,649-656; resnet_SGG_emb.py:240-256) -- */
+/* boxes [N,4] fp32 -> ixs, ixo [P] int64, rel_boxes [P,5] fp32 (col 0 = 0), masks [P,2,32,32] fp32,
+ * P = N*(N-1).  masks may be NULL. */
+int i2v_pair_build(const float* boxes, int num_boxes, float im_h, float im_w, float margin, int64_t* ixs,
+                   int64_t* ixo, float* rel_boxes, float* masks, cudaStream_t stream);
+
+/* ---- 8. Triplet top-k (lib/utils.py:609-626) ------------------------------------------------ */
+size_t i2v_triplet_topk_workspace_bytes(int num_pairs, int num_rel);
+/* rel_score [P,R]; conf [N]; classes [N] int64; boxes [N,4]; ixs/ixo [P] int64.
+ * record_out [top_k, 13] fp32 = (conf, cls_s, rel, cls_o, sub box x4, obj box x4, pair idx), rows past
+ * *count_out are zero.  Order: descending score, ties by lower flat index p*R+r. */
+int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
+                     const int64_t* ixs, const int64_t* ixo, int num_pairs, int num_rel, int top_k,
+                     float* record_out, int* count_out, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2VSGG_B200_H */

@@ -1,0 +1,245 @@
+"""The reference itself, as far as it can be run -- TEST INFRASTRUCTURE ONLY.
+
+Three things live here, all used to *pin* oracle/oracle.c and the CUDA path:
+
+* ``cpu_*``   -- ``oracle/_ref/libref_cpu.so``: the reference's own ``roi_align.c`` and
+  ``roi_pooling.c`` compiled unmodified (``make -C oracle ref``) behind the ``TH/TH.h`` shim.
+* ``cuda_*``  -- ``oracle/_ref/libref_cuda.so``: the reference's own ``roi_align_kernel.cu``,
+  ``roi_pooling_kernel.cu`` and ``nms_cuda_kernel.cu`` compiled unmodified for sm_100a; callable
+  only on a GPU box (device pointers come from torch tensors).
+* ``py_*``    -- the reference's Python (``nms_cpu.py``, ``proposal_layer.py`` ...) imported from
+  ``/root/reference`` behind an in-memory ``easydict`` shim.  ``/root/reference`` exists only in
+  the build container, so these are used by ``tests/golden/make_golden.py`` to write fixtures
+  and by tests marked ``needs_reference``; nothing on the GPU box calls them.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+import types
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = "/root/reference"
+
+_f = ctypes.c_float
+_i = ctypes.c_int
+_fp = ctypes.POINTER(ctypes.c_float)
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+
+
+def have_cpu_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_cpu.so"))
+
+
+def have_cuda_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_cuda.so"))
+
+
+def have_py_ref() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "lib", "model"))
+
+
+# ------------------------------------------------------------------ reference CPU C (unmodified)
+class _THFloatStorage(ctypes.Structure):
+    _fields_ = [("data", _fp), ("numel", ctypes.c_long)]
+
+
+class _THFloatTensor(ctypes.Structure):
+    _fields_ = [("data", _fp), ("size", ctypes.c_long * 4), ("ndim", _i), ("storage", _THFloatStorage)]
+
+
+def _th(a: np.ndarray) -> _THFloatTensor:
+    t = _THFloatTensor()
+    t.data = a.ctypes.data_as(_fp)
+    for d in range(4):
+        t.size[d] = a.shape[d] if d < a.ndim else 1
+    t.ndim = a.ndim
+    t.storage.data = t.data
+    t.storage.numel = a.size
+    return t
+
+
+_cpu = None
+
+
+def _cpu_lib():
+    global _cpu
+    if _cpu is None:
+        _cpu = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_cpu.so"))
+    return _cpu
+
+
+def cpu_roi_align_forward(feat, rois, gh, gw, scale) -> np.ndarray:
+    """roi_align.c:17-45 `roi_align_forward` (the cffi entry point itself)."""
+    feat = np.ascontiguousarray(feat, np.float32)
+    rois = np.ascontiguousarray(rois, np.float32).reshape(-1, 5)
+    out = np.zeros((rois.shape[0], feat.shape[1], gh, gw), np.float32)
+    tf, tr, to = _th(feat), _th(rois), _th(out)
+    rc = _cpu_lib().roi_align_forward(_i(gh), _i(gw), _f(scale), ctypes.byref(tf), ctypes.byref(tr), ctypes.byref(to))
+    assert rc == 1
+    return out
+
+
+def cpu_roi_pooling_forward_nhwc(feat_nhwc, rois, ph, pw, scale) -> np.ndarray:
+    """roi_pooling.c:4-104 `roi_pooling_forward` (NHWC input, batch 1, no argmax)."""
+    feat = np.ascontiguousarray(feat_nhwc, np.float32)
+    rois = np.ascontiguousarray(rois, np.float32).reshape(-1, 5)
+    out = np.zeros((rois.shape[0], feat.shape[3], ph, pw), np.float32)
+    tf, tr, to = _th(feat), _th(rois), _th(out)
+    rc = _cpu_lib().roi_pooling_forward(_i(ph), _i(pw), _f(scale), ctypes.byref(tf), ctypes.byref(tr), ctypes.byref(to))
+    assert rc == 1
+    return out
+
+
+# ------------------------------------------------------------------ reference CUDA kernels (unmodified)
+_cuda = None
+
+
+def _cuda_lib():
+    global _cuda
+    if _cuda is None:
+        _cuda = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_cuda.so"))
+    return _cuda
+
+
+def _stream():
+    import torch
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def cuda_roi_align_forward(feat, rois, gh, gw, scale):
+    """ROIAlignForwardLaucher (roi_align_kernel.cu:73-91) on torch CUDA tensors."""
+    import torch
+    N, C = rois.shape[0], feat.shape[1]
+    out = torch.zeros((N, C, gh, gw), device=feat.device, dtype=torch.float32)
+    _cuda_lib().ROIAlignForwardLaucher(_vp(feat.data_ptr()), _f(scale), _i(N), _i(feat.shape[2]), _i(feat.shape[3]),
+                                       _i(C), _i(gh), _i(gw), _vp(rois.data_ptr()), _vp(out.data_ptr()), _stream())
+    return out
+
+
+def cuda_roi_align_backward(top_diff, rois, feat_shape, gh, gw, scale):
+    """ROIAlignBackwardLaucher (roi_align_kernel.cu:145-162)."""
+    import torch
+    B, C, H, W = feat_shape
+    gin = torch.zeros((B, C, H, W), device=top_diff.device, dtype=torch.float32)
+    _cuda_lib().ROIAlignBackwardLaucher(_vp(top_diff.data_ptr()), _f(scale), _i(B), _i(rois.shape[0]), _i(H), _i(W),
+                                        _i(C), _i(gh), _i(gw), _vp(rois.data_ptr()), _vp(gin.data_ptr()), _stream())
+    return gin
+
+
+def cuda_roi_pool_forward(feat, rois, ph, pw, scale):
+    """ROIPoolForwardLaucher (roi_pooling_kernel.cu:95-125)."""
+    import torch
+    N, C = rois.shape[0], feat.shape[1]
+    out = torch.zeros((N, C, ph, pw), device=feat.device, dtype=torch.float32)
+    arg = torch.zeros((N, C, ph, pw), device=feat.device, dtype=torch.int32)
+    _cuda_lib().ROIPoolForwardLaucher(_vp(feat.data_ptr()), _f(scale), _i(N), _i(feat.shape[2]), _i(feat.shape[3]),
+                                      _i(C), _i(ph), _i(pw), _vp(rois.data_ptr()), _vp(out.data_ptr()),
+                                      _vp(arg.data_ptr()), _stream())
+    return out, arg
+
+
+def cuda_roi_pool_backward(top_diff, rois, argmax, feat_shape, ph, pw, scale):
+    """ROIPoolBackwardLaucher (roi_pooling_kernel.cu:205-234)."""
+    import torch
+    B, C, H, W = feat_shape
+    gin = torch.zeros((B, C, H, W), device=top_diff.device, dtype=torch.float32)
+    _cuda_lib().ROIPoolBackwardLaucher(_vp(top_diff.data_ptr()), _f(scale), _i(B), _i(rois.shape[0]), _i(H), _i(W),
+                                       _i(C), _i(ph), _i(pw), _vp(rois.data_ptr()), _vp(gin.data_ptr()),
+                                       _vp(argmax.data_ptr()), _stream())
+    return gin
+
+
+def cuda_nms(dets_sorted_host: np.ndarray, thresh: float):
+    """nms_cuda_compute (nms_cuda_kernel.cu:87-161): host boxes in, device keep/num out."""
+    import torch
+    dets = np.ascontiguousarray(dets_sorted_host, np.float32)
+    n, dim = dets.shape
+    keep = torch.zeros(n, device="cuda", dtype=torch.int32)
+    num = torch.zeros(1, device="cuda", dtype=torch.int32)
+    torch.cuda.synchronize()
+    _cuda_lib().nms_cuda_compute(_vp(keep.data_ptr()), _vp(num.data_ptr()), dets.ctypes.data_as(_fp), _i(n), _i(dim),
+                                 _f(thresh))
+    torch.cuda.synchronize()
+    return keep[: int(num.item())].cpu().numpy()
+
+
+# ------------------------------------------------------------------ reference Python (build container only)
+class _EasyDict(dict):
+    """What `from easydict import EasyDict` gives config.py:11: attribute access == item access, nested."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, _EasyDict):
+            v = _EasyDict(v)
+        super().__setitem__(k, v)
+        super().__setattr__(k, v)
+
+    __setattr__ = __setitem__
+
+
+_py_ready = False
+
+
+def _py_setup():
+    global _py_ready
+    if _py_ready:
+        return
+    if "easydict" not in sys.modules:
+        m = types.ModuleType("easydict")
+        m.EasyDict = _EasyDict
+        sys.modules["easydict"] = m
+    if not hasattr(np, "float"):      # lib/utils.py-era aliases some reference files still use
+        np.float = float
+    sys.path.insert(0, os.path.join(REF_ROOT, "lib"))
+    _py_ready = True
+
+
+def py_nms_cpu(dets: np.ndarray, thresh: float) -> np.ndarray:
+    """Executes lib/model/nms/nms_cpu.py:6-34 unmodified."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("_ref_nms_cpu", os.path.join(REF_ROOT, "lib/model/nms/nms_cpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.nms_cpu(torch.from_numpy(np.ascontiguousarray(dets, np.float32)), thresh).numpy()
+
+
+def py_generate_anchors(**kw) -> np.ndarray:
+    """Executes lib/model/rpn/generate_anchors.py:45-56 unmodified."""
+    _py_setup()
+    from model.rpn.generate_anchors import generate_anchors
+    return generate_anchors(**kw)
+
+
+def py_proposal_layer(cls_prob, bbox_pred, im_info, cfg_key="TEST", target=False, overrides=None):
+    """Executes _ProposalLayer.forward (lib/model/rpn/proposal_layer.py:49-163) unmodified on CPU tensors."""
+    _py_setup()
+    import torch
+    from model.utils.config import cfg
+    from model.rpn.proposal_layer import _ProposalLayer
+    for k, v in (overrides or {}).items():
+        cfg[cfg_key][k] = v
+    layer = _ProposalLayer(cfg.FEAT_STRIDE[0], cfg.ANCHOR_SCALES, cfg.ANCHOR_RATIOS)
+    with torch.no_grad():
+        out = layer((torch.from_numpy(cls_prob), torch.from_numpy(bbox_pred), torch.from_numpy(im_info), cfg_key),
+                    target)
+    return out.numpy()
+
+
+def py_bbox_transform_inv_clip(anchors, deltas, im_info):
+    """Executes bbox_transform.py:77-103 and :125-133 unmodified."""
+    _py_setup()
+    import torch
+    from model.rpn.bbox_transform import bbox_transform_inv, clip_boxes
+    B = deltas.shape[0]
+    p = bbox_transform_inv(torch.from_numpy(anchors), torch.from_numpy(deltas), B)
+    return clip_boxes(p, torch.from_numpy(im_info), B).numpy()
