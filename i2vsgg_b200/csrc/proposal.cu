@@ -74,6 +74,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 // Monotone map float -> uint32 whose ASCENDING order is the DESCENDING order of the floats.
 __device__ __forceinline__ unsigned desc_key(float f) {
     unsigned u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;  // -0 sorts as +0 (they compare equal; index order breaks the tie)
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
     return ~u;
 }

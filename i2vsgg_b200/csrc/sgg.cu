@@ -73,6 +73,7 @@ constexpr int kTopMax = 1024;  // largest supported top_k
 
 __device__ __forceinline__ unsigned topk_desc_key(float f) {
     unsigned u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;  // -0 ranks as +0
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     return ~u;
 }
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kTopThreads) triplet_topk_kernel(
         if (warp == 0) {
             // find the digit where the running count reaches s_need: 64 bins per lane
             const int per = (1 << bits[pass]) / 32;
+            const unsigned need = s_need;  // read by every lane before the owning lane rewrites it below
             unsigned sum = 0;
             for (int q = 0; q < per; ++q) sum += hist[lane * per + q];
             unsigned incl = sum;
@@ -131,9 +133,9 @@ __global__ void __launch_bounds__(kTopThreads) triplet_topk_kernel(
                 unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            unsigned need = s_need;
             unsigned excl = incl - sum;
             bool mine = (excl < need) && (incl >= need);
+            __syncwarp();
             if (mine) {
                 unsigned run = excl;
                 for (int q = 0; q < per; ++q) {

@@ -1,0 +1,172 @@
+"""GPU parity tests (B200 box): proposal decode, sort, NMS and the fused proposal layer through the C ABI against the
+oracle (bit-exact indices) and against the golden vectors written from the reference's own Python."""
+import numpy as np
+import pytest
+import torch
+
+from i2vsgg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from i2vsgg_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.mark.parametrize("seed,n,thr", [(1, 1, 0.7), (2, 37, 0.7), (3, 300, 0.7), (4, 2000, 0.7), (5, 2000, 0.3),
+                                        (6, 6000, 0.7), (7, 12000, 0.7)])
+def test_nms_keep_list_bit_exact_vs_reference(ops, golden, seed, n, thr):
+    dets = synth.nms_dets(seed, n)
+    keep = ops.nms_dets(cuda(dets), thr)
+    assert keep.dtype == torch.int32
+    assert np.array_equal(keep.cpu().numpy(), golden[f"nms_keep_{seed}_{n}_{thr}"])
+
+
+def test_nms_wrapper_and_gpu_entry_points(ops, orc, golden):
+    import i2vsgg_b200
+    i2vsgg_b200.install_as_model()
+    from model.nms.nms_wrapper import nms
+    from model.nms.nms_gpu import nms_gpu
+    from model.roi_layers import nms as c_nms
+    dets = synth.nms_dets(3, 300)
+    assert nms(torch.zeros((0, 5), device="cuda"), 0.7) == []
+    assert np.array_equal(nms(cuda(dets), 0.7).cpu().numpy(), golden["nms_keep_3_300_0.7"])
+    order = np.argsort(-dets[:, 4], kind="stable")
+    k = nms_gpu(cuda(dets[order]), 0.7)
+    assert k.shape[1] == 1
+    assert np.array_equal(order[k.view(-1).cpu().numpy()], golden["nms_keep_3_300_0.7"])
+    k2 = c_nms(cuda(dets[:, :4]), cuda(dets[:, 4]), 0.7)
+    assert k2.dtype == torch.int64 and np.array_equal(k2.cpu().numpy(), golden["nms_keep_3_300_0.7"])
+
+
+def test_nms_sorted_batched_max_keep_and_spill(ops, orc):
+    # batch of independent sets, early stop, and more survivors than the shared-memory cache holds
+    sets = [synth.nms_dets(40 + i, 3000) for i in range(3)]
+    sets = [d[np.argsort(-d[:, 4], kind="stable")] for d in sets]
+    boxes = np.stack(sets)
+    for max_keep in (0, 1, 77):
+        keep, num = ops.nms_sorted(cuda(boxes), 0.7, max_keep)
+        for b in range(3):
+            want = orc.nms_sorted(sets[b], 0.7, max_keep)
+            assert int(num[b]) == want.size
+            assert np.array_equal(keep[b, : want.size].cpu().numpy(), want)
+    rng = np.random.default_rng(3)       # 6000 disjoint boxes: every one survives -> spill path
+    n = 6000
+    gx, gy = np.meshgrid(np.arange(100), np.arange(60))
+    b0 = np.stack([gx.ravel() * 10, gy.ravel() * 10, gx.ravel() * 10 + 5, gy.ravel() * 10 + 5,
+                   np.linspace(1, 0, n)], 1).astype(np.float32)
+    keep, num = ops.nms_sorted(cuda(b0), 0.5)
+    assert keep.numel() == n and np.array_equal(keep.cpu().numpy(), np.arange(n))
+
+
+def test_nms_legacy_entry_point(ops, orc):
+    import ctypes
+    from i2vsgg_b200 import _lib
+    lib = _lib.load()
+    d = synth.nms_dets(5, 2000)
+    d = np.ascontiguousarray(d[np.argsort(-d[:, 4], kind="stable")])
+    keep = torch.zeros(2000, dtype=torch.int32, device="cuda")
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    lib.nms_cuda_compute(ctypes.c_void_p(keep.data_ptr()), ctypes.c_void_p(num.data_ptr()),
+                         ctypes.c_void_p(d.ctypes.data), 2000, 5, 0.7)        # host boxes, as nms_cuda_kernel.cu:99
+    want = orc.nms_sorted(d, 0.7)
+    assert int(num.item()) == want.size and np.array_equal(keep[: want.size].cpu().numpy(), want)
+    dd = cuda(d)
+    lib.nms_cuda_compute(ctypes.c_void_p(keep.data_ptr()), ctypes.c_void_p(num.data_ptr()),
+                         ctypes.c_void_p(dd.data_ptr()), 2000, 5, 0.7)        # device boxes work too
+    assert int(num.item()) == want.size and np.array_equal(keep[: want.size].cpu().numpy(), want)
+
+
+def test_decode_and_sort_stages(ops, orc, golden):
+    cls, reg = synth.rpn_outputs(12, batch=1)
+    info = synth.im_info(1)
+    boxes, scores, order = ops.proposal_stages(cuda(cls), cuda(reg), cuda(info), cuda(synth.BASE_ANCHORS), 16)
+    wb, wsc = orc.proposal_decode(cls, reg, info, synth.BASE_ANCHORS)
+    assert np.array_equal(scores.cpu().numpy(), wsc)
+    assert np.array_equal(boxes.cpu().numpy(), wb)                      # same roundings as the oracle: bit-exact
+    np.testing.assert_allclose(boxes.cpu().numpy(), golden["decode_b1"], rtol=2e-6, atol=2e-4)   # vs torch (exp ulp)
+    assert np.array_equal(order.cpu().numpy()[0], np.argsort(-wsc[0], kind="stable"))
+
+
+def test_sort_is_stable_with_ties_and_negatives(ops):
+    rng = np.random.default_rng(2)
+    n = 5000
+    score = rng.choice(np.array([-2.5, -0.0, 0.0, 0.25, 0.25, 1e-30, 3.0, -1e-30], np.float32), n)
+    dets = np.concatenate([rng.uniform(0, 100, (n, 4)).astype(np.float32), score[:, None]], 1)
+    # thresh 2.0 > any IoU: nothing is suppressed, the keep list IS the sort order
+    keep = ops.nms_dets(cuda(dets), 2.0).cpu().numpy()
+    want = np.argsort(-score.astype(np.float64) + 0.0, kind="stable")
+    assert np.array_equal(score[keep], score[want])
+    for v in np.unique(score):           # equal scores keep their original order (lower index first)
+        idx = keep[score[keep] == v]
+        assert np.all(np.diff(idx) > 0)
+
+
+@pytest.mark.parametrize("key,seed,batch,pre,post", [("prop_test_b2", 11, 2, 6000, 300),
+                                                     ("prop_train_b1", 12, 1, 12000, 2000),
+                                                     ("prop_train_target_b1", 12, 1, 12000, 128)])
+def test_proposal_layer_vs_reference_and_oracle(ops, orc, golden, key, seed, batch, pre, post):
+    cls, reg = synth.rpn_outputs(seed, batch=batch)
+    info = synth.im_info(batch)
+    out, counts = ops.proposal_forward(cuda(cls), cuda(reg), cuda(info), cuda(synth.BASE_ANCHORS), 16, pre, post, 0.7,
+                                       return_counts=True)
+    want = orc.proposal_layer(cls, reg, info, pre, post, 0.7)
+    assert np.array_equal(out.cpu().numpy(), want)                      # bit-exact vs the oracle
+    np.testing.assert_allclose(out.cpu().numpy(), golden[key], rtol=2e-6, atol=2e-4)   # vs the reference's Python
+    assert np.array_equal(counts.cpu().numpy(), (want[:, :, 1:].any(-1)).sum(1))
+
+
+def test_proposal_layer_module(ops, orc):
+    import i2vsgg_b200
+    i2vsgg_b200.install_as_model()
+    from model.rpn.proposal_layer import _ProposalLayer
+    from model.utils.config import cfg
+    cls, reg = synth.rpn_outputs(13, batch=2)
+    info = synth.im_info(2)
+    layer = _ProposalLayer(cfg.FEAT_STRIDE[0], cfg.ANCHOR_SCALES, cfg.ANCHOR_RATIOS)
+    out = layer((cuda(cls), cuda(reg), cuda(info), "TEST"))
+    assert out.shape == (2, 300, 5)
+    assert np.array_equal(out.cpu().numpy(), orc.proposal_layer(cls, reg, info, 6000, 300, 0.7))
+    out = layer((cuda(cls), cuda(reg), cuda(info), "TRAIN"), target=True)
+    assert np.array_equal(out.cpu().numpy(), orc.proposal_layer(cls, reg, info, 12000, 128, 0.7))
+
+
+def test_proposal_small_map_and_padding(ops, orc):
+    # 5x7 map: 315 anchors < pre_nms_topN, fewer survivors than post_nms_topN -> zero-padded rows keep the frame id
+    cls, reg = synth.rpn_outputs(14, batch=3, h=5, w=7, clusters=3)
+    info = synth.im_info(3)
+    out = ops.proposal_forward(cuda(cls), cuda(reg), cuda(info), cuda(synth.BASE_ANCHORS), 16, 6000, 300, 0.7)
+    want = orc.proposal_layer(cls, reg, info, 6000, 300, 0.7)
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert (out[:, -1, 1:] == 0).all() and (out[:, -1, 0].cpu() == torch.arange(3.0)).all()
+
+
+def test_nms_properties_at_full_size(ops):
+    # size-independent properties at BASELINE config 2 size: kept boxes are pairwise below the threshold, every
+    # dropped box overlaps an earlier kept one, and running NMS on the survivors keeps them all (idempotence)
+    d = synth.nms_dets(77, 12000)
+    d = d[np.argsort(-d[:, 4], kind="stable")]
+    keep, _ = ops.nms_sorted(cuda(d), 0.7)
+    kept = d[keep.cpu().numpy()]
+    again, _ = ops.nms_sorted(cuda(kept), 0.7)
+    assert again.numel() == kept.shape[0]
+    k = torch.from_numpy(kept[:, :4]).cuda()
+    area = (k[:, 2] - k[:, 0] + 1) * (k[:, 3] - k[:, 1] + 1)
+    iw = (torch.minimum(k[:, None, 2], k[None, :, 2]) - torch.maximum(k[:, None, 0], k[None, :, 0]) + 1).clamp(min=0)
+    ih = (torch.minimum(k[:, None, 3], k[None, :, 3]) - torch.maximum(k[:, None, 1], k[None, :, 1]) + 1).clamp(min=0)
+    iou = iw * ih / (area[:, None] + area[None, :] - iw * ih)
+    iou.fill_diagonal_(0)
+    assert float(iou.max()) <= 0.7 + 1e-6

@@ -1,0 +1,249 @@
+"""GPU parity tests (run on the B200 box): RoIAlign / RoIPool forward+backward through the C ABI against the CPU
+oracle, and -- when oracle/_ref/libref_cuda.so travelled with the snapshot -- against the reference's own .cu
+kernels compiled unmodified for sm_100a."""
+import numpy as np
+import pytest
+import torch
+
+from i2vsgg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SCALE = 1.0 / 16
+# north_star: RoIAlign features and gradients within 1e-5 relative in fp32
+RTOL = 1e-5
+
+
+def close(got, want, rtol=RTOL):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    atol = rtol * float(np.abs(want).max()) if want.size else 0.0
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from i2vsgg_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+CASES = [  # (batch, channels, H, W, num_rois)
+    (1, 32, 38, 63, 60),       # config-1 geometry, fewer channels so the oracle is quick
+    (3, 16, 38, 63, 97),
+    (2, 48, 20, 31, 50),       # runtime-width code path
+]
+
+
+@pytest.mark.parametrize("pool", ["none", "avg", "max"])
+@pytest.mark.parametrize("impl", ["gather", "plane"])
+@pytest.mark.parametrize("case", CASES)
+def test_roi_align_forward(ops, orc, case, impl, pool):
+    B, C, H, W, N = case
+    feat = synth.feature_map(100 + B, B, C, H, W)
+    rois = synth.rois(200 + N, N, batch=B)
+    if W != 63:
+        rois[:, 1:] *= W / 63.0
+    want = orc.roi_align_pooled_forward(feat, rois, 7, 7, SCALE, pool, nthreads=8)
+    got = ops.roi_align_forward(cuda(feat), cuda(rois), 7, 7, SCALE, pool, impl)
+    if impl == "gather" and pool in ("none", "avg", "max"):
+        # the gather kernel evaluates the weights in double like roi_align_kernel.cu:64-67: bit-exact
+        assert np.array_equal(got.cpu().numpy(), want)
+    close(got, want)
+
+
+@pytest.mark.parametrize("pool,p", [("none", 7), ("none", 4), ("avg", 7), ("max", 7), ("avg", 3)])
+def test_roi_align_forward_other_sizes_and_bad_batch(ops, orc, pool, p):
+    feat = synth.feature_map(7, 2, 8, 25, 40)
+    rois = synth.rois(8, 33, batch=2)
+    rois[:, 1:] *= 0.6
+    want = orc.roi_align_pooled_forward(feat, rois, p, p, SCALE, pool)
+    rois_bad = rois.copy()
+    rois_bad[5, 0] = 7      # frame index outside the batch -> zero rows by contract
+    rois_bad[9, 0] = -1
+    want[5] = 0
+    want[9] = 0
+    got = ops.roi_align_forward(cuda(feat), cuda(rois_bad), p, p, SCALE, pool)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_roi_align_plane_zero_fills_bad_batch(ops, orc):
+    feat = synth.feature_map(9, 2, 16, 38, 63)
+    rois = synth.rois(10, 40, batch=2)
+    want = orc.roi_align_pooled_forward(feat, rois, 7, 7, SCALE, "avg")
+    rois[3, 0] = 2
+    want[3] = 0
+    got = ops.roi_align_forward(cuda(feat), cuda(rois), 7, 7, SCALE, "avg", "plane")
+    close(got, want)
+    assert float(got[3].abs().max()) == 0.0
+
+
+def test_roi_align_empty(ops):
+    feat = cuda(synth.feature_map(1, 1, 16, 38, 63))
+    out = ops.roi_align_forward(feat, torch.zeros((0, 5), device="cuda"), 7, 7, SCALE, "avg")
+    assert out.shape == (0, 16, 7, 7)
+    g = ops.roi_align_backward(torch.zeros((0, 16, 7, 7), device="cuda"), None, torch.zeros((0, 5), device="cuda"),
+                               (1, 16, 38, 63), 7, 7, SCALE, "avg")
+    assert float(g.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("pool", ["none", "avg", "max"])
+@pytest.mark.parametrize("impl", ["gather", "auto"])
+@pytest.mark.parametrize("case", CASES)
+def test_roi_align_backward(ops, orc, case, impl, pool):
+    B, C, H, W, N = case
+    feat = synth.feature_map(100 + B, B, C, H, W)
+    rois = synth.rois(200 + N, N, batch=B)
+    if W != 63:
+        rois[:, 1:] *= W / 63.0
+    g = np.random.default_rng(5).standard_normal((N, C, 7, 7)).astype(np.float32)
+    want = orc.roi_align_pooled_backward(g, feat, rois, 7, 7, SCALE, pool, nthreads=8)
+    got = ops.roi_align_backward(cuda(g), cuda(feat), cuda(rois), feat.shape, 7, 7, SCALE, pool, impl)
+    close(got, want)
+
+
+def test_roi_align_autograd_module(ops, orc):
+    import i2vsgg_b200
+    i2vsgg_b200.install_as_model()
+    from model.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+    feat = synth.feature_map(3, 2, 16, 38, 63)
+    rois = synth.rois(4, 30, batch=2)
+    g = np.random.default_rng(6).standard_normal((30, 16, 7, 7)).astype(np.float32)
+    for mod, pool in ((RoIAlign, "none"), (RoIAlignAvg, "avg"), (RoIAlignMax, "max")):
+        f = cuda(feat).requires_grad_(True)
+        out = mod(7, 7, SCALE)(f, cuda(rois))
+        out.backward(cuda(g))
+        close(out, orc.roi_align_pooled_forward(feat, rois, 7, 7, SCALE, pool))
+        close(f.grad, orc.roi_align_pooled_backward(g, feat, rois, 7, 7, SCALE, pool))
+
+
+@pytest.mark.parametrize("mode", ["flat", "plane"])
+def test_roi_pool_forward_backward(ops, orc, mode):
+    B, C, H, W, N = 2, 24, 38, 63, 70
+    feat = synth.feature_map(11, B, C, H, W)
+    rois = synth.rois(12, N, batch=B)          # includes degenerate and past-the-edge RoIs
+    g = np.random.default_rng(7).standard_normal((N, C, 7, 7)).astype(np.float32)
+    if mode == "flat":
+        want, warg = orc.roi_pool_forward(feat, rois, 7, 7, SCALE, nthreads=8)
+        wgrad = orc.roi_pool_backward(g, rois, warg, feat.shape, 7, 7, SCALE)
+        am = ops.ARGMAX_FLAT
+    else:
+        want, warg = orc.c_roi_pool_forward(feat, rois, 7, 7, SCALE, nthreads=8)
+        wgrad = orc.c_roi_pool_backward(g, rois, warg, feat.shape, 7, 7)
+        am = ops.ARGMAX_PLANE
+    out, arg = ops.roi_pool_forward(cuda(feat), cuda(rois), 7, 7, SCALE, am)
+    assert np.array_equal(out.cpu().numpy(), want)          # max and index: bit-exact
+    assert np.array_equal(arg.cpu().numpy(), warg)
+    grad = ops.roi_pool_backward(cuda(g), cuda(rois), arg, feat.shape, 7, 7, SCALE, am)
+    close(grad, wgrad)
+
+
+def test_roi_pool_modules(ops, orc):
+    import i2vsgg_b200
+    i2vsgg_b200.install_as_model()
+    from model.roi_pooling.modules.roi_pool import _RoIPooling
+    from model.roi_layers import ROIAlign, ROIPool
+    feat = synth.feature_map(13, 2, 8, 38, 63)
+    rois = synth.rois(14, 25, batch=2, degenerate=0)
+    g = np.random.default_rng(8).standard_normal((25, 8, 7, 7)).astype(np.float32)
+    f = cuda(feat).requires_grad_(True)
+    out = _RoIPooling(7, 7, SCALE)(f, cuda(rois))
+    out.backward(cuda(g))
+    want, warg = orc.roi_pool_forward(feat, rois, 7, 7, SCALE)
+    assert np.array_equal(out.detach().cpu().numpy(), want)
+    close(f.grad, orc.roi_pool_backward(g, rois, warg, feat.shape, 7, 7, SCALE))
+    f = cuda(feat).requires_grad_(True)
+    out = ROIPool((7, 7), SCALE)(f, cuda(rois))
+    out.backward(cuda(g))
+    want, warg = orc.c_roi_pool_forward(feat, rois, 7, 7, SCALE)
+    assert np.array_equal(out.detach().cpu().numpy(), want)
+    close(f.grad, orc.c_roi_pool_backward(g, rois, warg, feat.shape, 7, 7))
+    for sr in (0, 2):
+        f = cuda(feat).requires_grad_(True)
+        out = ROIAlign((7, 7), SCALE, sr)(f, cuda(rois))
+        out.backward(cuda(g))
+        close(out, orc.c_roi_align_forward(feat, rois, 7, 7, SCALE, sr), rtol=1e-5)
+        close(f.grad, orc.c_roi_align_backward(g, rois, feat.shape, 7, 7, SCALE, sr), rtol=1e-5)
+
+
+def test_c_ops_match_torchvision_cuda(ops):
+    tv = pytest.importorskip("torchvision.ops")
+    feat = cuda(synth.feature_map(15, 2, 16, 38, 63))
+    rois = cuda(synth.rois(16, 40, batch=2, degenerate=0))
+    want = tv.roi_align(feat, rois, (7, 7), SCALE, 0, aligned=False)
+    got = ops.c_roi_align_forward(feat, rois, 7, 7, SCALE, 0)
+    close(got, want.cpu().numpy(), rtol=1e-5)
+    want = tv.roi_pool(feat, rois, (7, 7), SCALE)
+    got, _ = ops.roi_pool_forward(feat, rois, 7, 7, SCALE, ops.ARGMAX_PLANE)
+    assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------- against the reference's own CUDA kernels
+def _ref():
+    from oracle import ref
+    if not ref.have_cuda_ref():
+        pytest.skip("oracle/_ref/libref_cuda.so did not travel with the snapshot")
+    return ref
+
+
+def test_reference_kernels_pin_the_oracle_and_us(ops, orc):
+    ref = _ref()
+    feat = synth.feature_map(21, 2, 16, 38, 63)
+    rois = synth.rois(22, 64, batch=2)
+    f, r = cuda(feat), cuda(rois)
+    # forward: reference kernel vs oracle vs ours
+    ref_out = ref.cuda_roi_align_forward(f, r, 8, 8, SCALE).cpu().numpy()
+    want = orc.roi_align_forward(feat, rois, 8, 8, SCALE)
+    # the reference's GPU build contracts `ph * bin + start` (roi_align_kernel.cu:44-45) into an FMA, its CPU twin
+    # (roi_align.c:106-107, which the oracle pins bit for bit) does not: sample positions differ in the last bit,
+    # i.e. by ~2e-6 cells, which moves values by up to ~2e-5.  That is the reference's own CPU/GPU spread.
+    close(ref_out, want, rtol=1e-4)
+    ours = ops.roi_align_forward(f, r, 8, 8, SCALE, "none", "gather")
+    close(ours, ref_out, rtol=1e-4)
+    # backward
+    g = np.random.default_rng(9).standard_normal((64, 16, 8, 8)).astype(np.float32)
+    ref_g = ref.cuda_roi_align_backward(cuda(g), r, feat.shape, 8, 8, SCALE).cpu().numpy()
+    close(ref_g, orc.roi_align_backward(g, rois, feat.shape, 8, 8, SCALE), rtol=1e-4)
+    close(ops.roi_align_backward(cuda(g), None, r, feat.shape, 8, 8, SCALE, "none"), ref_g, rtol=1e-4)
+    # RoIPool fwd/bwd
+    ref_p, ref_a = ref.cuda_roi_pool_forward(f, r, 7, 7, SCALE)
+    wp, wa = orc.roi_pool_forward(feat, rois, 7, 7, SCALE)
+    assert np.array_equal(ref_p.cpu().numpy(), wp) and np.array_equal(ref_a.cpu().numpy(), wa)
+    g7 = np.random.default_rng(10).standard_normal((64, 16, 7, 7)).astype(np.float32)
+    ref_pg = ref.cuda_roi_pool_backward(cuda(g7), r, ref_a, feat.shape, 7, 7, SCALE).cpu().numpy()
+    close(ref_pg, orc.roi_pool_backward(g7, rois, wa, feat.shape, 7, 7, SCALE))
+    close(ops.roi_pool_backward(cuda(g7), r, ref_a, feat.shape, 7, 7, SCALE, ops.ARGMAX_FLAT), ref_pg)
+
+
+def test_legacy_launchers(ops, orc):
+    import ctypes
+    from i2vsgg_b200 import _lib
+    lib = _lib.load()
+    feat = synth.feature_map(31, 2, 8, 38, 63)
+    rois = synth.rois(32, 20, batch=2)
+    f, r = cuda(feat), cuda(rois)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    out = torch.empty((20, 8, 8, 8), device="cuda")
+    assert lib.ROIAlignForwardLaucher(P(f), SCALE, 20, 38, 63, 8, 8, 8, P(r), P(out), s) == 1
+    assert np.array_equal(out.cpu().numpy(), orc.roi_align_forward(feat, rois, 8, 8, SCALE))
+    g = np.random.default_rng(11).standard_normal((20, 8, 8, 8)).astype(np.float32)
+    gin = torch.zeros((2, 8, 38, 63), device="cuda")
+    assert lib.ROIAlignBackwardLaucher(P(cuda(g)), SCALE, 2, 20, 38, 63, 8, 8, 8, P(r), P(gin), s) == 1
+    close(gin, orc.roi_align_backward(g, rois, feat.shape, 8, 8, SCALE))
+    po = torch.empty((20, 8, 7, 7), device="cuda")
+    pa = torch.empty((20, 8, 7, 7), device="cuda", dtype=torch.int32)
+    assert lib.ROIPoolForwardLaucher(P(f), SCALE, 20, 38, 63, 8, 7, 7, P(r), P(po), P(pa), s) == 1
+    wp, wa = orc.roi_pool_forward(feat, rois, 7, 7, SCALE)
+    assert np.array_equal(po.cpu().numpy(), wp) and np.array_equal(pa.cpu().numpy(), wa)
+    g7 = np.random.default_rng(12).standard_normal((20, 8, 7, 7)).astype(np.float32)
+    pg = torch.full((2, 8, 38, 63), 7.0, device="cuda")
+    assert lib.ROIPoolBackwardLaucher(P(cuda(g7)), SCALE, 2, 20, 38, 63, 8, 7, 7, P(r), P(pg), P(pa), s) == 1
+    close(pg, orc.roi_pool_backward(g7, rois, wa, feat.shape, 7, 7, SCALE))
