@@ -102,6 +102,22 @@ struct alignas(16) LatticeRoi {
     unsigned valid_y;     // bit p set <=> !(h < 0 || h >= H) for lattice row p (roi_align_kernel.cu:54)
     unsigned valid_x;
     unsigned flags;       // bit0: y starts strictly increasing over valid rows; bit1: same for x
+    // duplicate structure of the start cells (starts are non-decreasing), used by the plane backward:
+    unsigned y_runpos;    // nibble p: how many earlier valid rows share row p's start cell (position in its run)
+    unsigned y_maxrun;    // 1 + largest nibble of y_runpos (0 when no row is valid)
+    unsigned x_same;      // bit p: valid column p has the same start cell as valid column p-1
+    unsigned pad_;
+};
+
+// What the forward plane kernel needs of one RoI (lattices of up to 8 points per axis): byte offsets into the
+// [cell][16 channels] shared-memory planes and weights with validity (and the avg pool's 1/4) already folded in.
+struct alignas(16) PlaneTab {
+    int xoff[8];    // start column * 64 bytes
+    float wxl[8];   // weight of the left cell  (1 - frac) * scale, 0 for an out-of-range lattice column
+    float wxr[8];   // weight of the right cell  frac * scale
+    int yoff[8];    // start row * W * 64 bytes
+    float wy0[8];   // weight of the upper row (1 - frac), 0 for an out-of-range lattice row
+    float wy1[8];   // weight of the lower row  frac
 };
 
 }  // namespace i2v

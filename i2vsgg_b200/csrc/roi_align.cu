@@ -53,7 +53,7 @@ __device__ __forceinline__ void lattice_axis(float lo, float hi, int G, int exte
 
 __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois, int batch, int H, int W, int GH,
                                     int GW, float scale, LatticeRoi* __restrict__ tab, int* __restrict__ roi_batch,
-                                    int* __restrict__ counts) {
+                                    int* __restrict__ counts, PlaneTab* __restrict__ ptab, float ptab_scale) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= num_rois) return;
     const float* r = rois + (size_t)n * 5;
@@ -65,7 +65,42 @@ __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois
     lattice_axis(__fmul_rn(r[2], scale), __fmul_rn(r[4], scale), GH, H, t.y, t.valid_y, incy);
     t.batch = in_batch ? b : -1;
     t.flags = (incy ? 1u : 0u) | (incx ? 2u : 0u);
+    {
+        unsigned runpos = 0, maxrun = 0, same = 0;
+        int prev = -1, run = 0, prevx = -1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {   // the plane kernels handle lattices of up to 8 points per axis
+            if ((t.valid_y >> p) & 1u) {
+                run = (t.y.start[p] == prev) ? run + 1 : 0;
+                prev = t.y.start[p];
+                runpos |= (unsigned)run << (4 * p);
+                maxrun = max(maxrun, (unsigned)run + 1u);
+            }
+            if ((t.valid_x >> p) & 1u) {
+                if (t.x.start[p] == prevx) same |= 1u << p;
+                prevx = t.x.start[p];
+            }
+        }
+        t.y_runpos = runpos;
+        t.y_maxrun = maxrun;
+        t.x_same = same;
+        t.pad_ = 0;
+    }
     tab[n] = t;
+    if (ptab) {  // the forward plane kernel's view: byte offsets into the [cell][16] planes and ready-to-use weights
+        PlaneTab q;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            bool okx = (t.valid_x >> p) & 1u, oky = (t.valid_y >> p) & 1u;
+            q.xoff[p] = t.x.start[p] * (16 * 4);
+            q.wxl[p] = okx ? (1.f - t.x.frac[p]) * ptab_scale : 0.f;
+            q.wxr[p] = okx ? t.x.frac[p] * ptab_scale : 0.f;
+            q.yoff[p] = t.y.start[p] * W * (16 * 4);
+            q.wy0[p] = oky ? 1.f - t.y.frac[p] : 0.f;
+            q.wy1[p] = oky ? t.y.frac[p] : 0.f;
+        }
+        ptab[n] = q;
+    }
     // RoIs whose batch index is out of range are listed in the extra bucket `batch` (their rows are zero-filled)
     if (roi_batch) roi_batch[n] = in_batch ? b : batch;
     if (counts) atomicAdd(&counts[in_batch ? b : batch], 1);
@@ -221,10 +256,10 @@ __global__ void __launch_bounds__(256) lattice_bwd_gather_kernel(const float* __
 
 // ------------------------------------------------------------------------------------------ plane forward
 constexpr int kPlaneK = 16;        // channels per CTA
-constexpr int kPlaneWarps = 8;     // warps per CTA
+constexpr int kPlaneWarps = 16;    // warps per CTA
 constexpr int kPlaneThreads = kPlaneWarps * 32;
-constexpr int kFillCells = 768;    // cells per fill round
-constexpr int kFillPitch = 770;    // == 2 (mod 32): the transposing read of a round is bank-conflict free
+constexpr int kFillCells = 384;    // cells per fill round
+constexpr int kFillPitch = 386;    // == 2 (mod 32): the transposing read of a round is bank-conflict free
 
 __device__ __forceinline__ void bulk_store_commit(float* gdst, const float* ssrc, unsigned bytes) {
     unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
@@ -232,28 +267,25 @@ __device__ __forceinline__ void bulk_store_commit(float* gdst, const float* ssrc
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// The table of one RoI as it sits in registers while the previous RoI is being computed (G <= 8).
-struct RawLattice {
-    int4 ys[2], yf[2], xs[2], xf[2], tail;
-    int n;
-};
-__device__ __forceinline__ void load_raw(RawLattice& r, const LatticeRoi* __restrict__ tab,
-                                         const int* __restrict__ order, int li) {
-    r.n = __ldg(order + li);
-    const int4* q = reinterpret_cast<const int4*>(tab + r.n);
-    r.ys[0] = __ldg(q + 0);  r.ys[1] = __ldg(q + 1);
-    r.yf[0] = __ldg(q + 4);  r.yf[1] = __ldg(q + 5);
-    r.xs[0] = __ldg(q + 8);  r.xs[1] = __ldg(q + 9);
-    r.xf[0] = __ldg(q + 12); r.xf[1] = __ldg(q + 13);
-    r.tail = __ldg(q + 16);
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+                 : "memory");
 }
-__device__ __forceinline__ int pick(const int4 (&a)[2], int p) {  // p is a compile-time constant after unrolling
-    const int4& v = a[p >> 2];
-    return (p & 3) == 0 ? v.x : (p & 3) == 1 ? v.y : (p & 3) == 2 ? v.z : v.w;
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // P = pooled size (output is P x P); lattice G = P (+1 when a pool follows); WT = compile-time map width (0: runtime).
@@ -263,18 +295,20 @@ __device__ __forceinline__ int pick(const int4 (&a)[2], int p) {  // p is a comp
 // [16][P*P] tile -- which is contiguous in the NCHW output -- leaves through a TMA bulk store.
 template <int P, int POOL, int WT>
 __global__ void __launch_bounds__(kPlaneThreads, 1)
-    lattice_fwd_plane_kernel(const float* __restrict__ feat, const LatticeRoi* __restrict__ tab,
+    lattice_fwd_plane_kernel(const float* __restrict__ feat, const PlaneTab* __restrict__ ptab,
                              const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ out,
                              int batch, int C, int H, int Wrt, int split) {
     constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
     constexpr int NOUT = P * P;
     constexpr int TILE = kPlaneK * NOUT;  // floats per staged output tile
-    static_assert(G <= 8, "register tables hold 8 lattice points per axis");
+    constexpr int TABF = (int)(sizeof(PlaneTab) / sizeof(float));
+    static_assert(G <= 8, "tables hold 8 lattice points per axis");
     extern __shared__ __align__(128) float smem[];
     const int W = WT ? WT : Wrt;
     const int HW = H * W;
-    float* planes = smem;                        // [HW][16]
-    float* stage = smem + (size_t)HW * kPlaneK;  // [warps][2][TILE]; doubles as the fill scratch
+    float* planes = smem;                            // [HW][16]
+    float* stage = smem + (size_t)HW * kPlaneK;      // [warps][TILE]; doubles as the fill scratch [2][16][386]
+    float* tabs = stage + (size_t)kPlaneWarps * TILE;  // [warps][2][sizeof(PlaneTab)]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctiles = C / kPlaneK;
@@ -293,67 +327,97 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
         return;
     }
 
-    // ---- fill: 16 planes, global [c][cell] -> shared [cell][16], through a [16][770] scratch ----
+    // ---- fill: 16 planes, global [c][cell] -> shared [cell][16].  Rounds of 384 cells stream through a double
+    // buffered [16][386] scratch with cp.async, so the copy of round r+1 overlaps the transposition of round r ----
     {
         const float* src = feat + ((size_t)b * C + (size_t)ct * kPlaneK) * HW;
-        for (int c0 = 0; c0 < HW; c0 += kFillCells) {
+        const int rounds = ceil_div(HW, kFillCells);
+        auto issue = [&](int r) {
+            float* scr = stage + (r & 1) * (kPlaneK * kFillPitch);
+            const int c0 = r * kFillCells;
             const int ncell = min(kFillCells, HW - c0);
             for (int i = tid; i < kPlaneK * kFillCells; i += kPlaneThreads) {
                 int c = i / kFillCells, x = i - c * kFillCells;
-                if (x < ncell) stage[c * kFillPitch + x] = __ldg(src + (size_t)c * HW + c0 + x);
+                if (x < ncell) cp_async4(scr + c * kFillPitch + x, src + (size_t)c * HW + c0 + x);
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        for (int r = 0; r < rounds; ++r) {
+            if (r + 1 < rounds) {
+                issue(r + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
             __syncthreads();
+            const float* scr = stage + (r & 1) * (kPlaneK * kFillPitch);
+            const int c0 = r * kFillCells;
+            const int ncell = min(kFillCells, HW - c0);
             for (int i = tid; i < kPlaneK * kFillCells; i += kPlaneThreads) {
                 int c = i & (kPlaneK - 1), x = i >> 4;
-                if (x < ncell) planes[(size_t)(c0 + x) * kPlaneK + c] = stage[c * kFillPitch + x];
+                if (x < ncell) planes[(size_t)(c0 + x) * kPlaneK + c] = scr[c * kFillPitch + x];
             }
             __syncthreads();
         }
     }
 
     const int c = lane & 15, dx = lane >> 4;
-    const char* pl0 = reinterpret_cast<const char*>(planes + c + dx * kPlaneK);  // row hs, this lane's column
+    // byte address (shared window) of this lane's channel in cell 0, row 0, already shifted to its column
+    const unsigned lane_base = (unsigned)__cvta_generic_to_shared(planes + c + dx * kPlaneK);
     const int row_bytes = W * kPlaneK * (int)sizeof(float);
-    float* my_stage = stage + (size_t)warp * 2 * TILE;
-    int buf = 0;
+    float* my_stage = stage + (size_t)warp * TILE;
+    float* my_tabs = tabs + (size_t)warp * 2 * TABF;
 
     int li = list_lo + gwarp;
-    RawLattice cur;
-    if (li < list_hi) load_raw(cur, tab, order, li);
+    int n_cur = 0, n_next = 0;
+    if (li < list_hi) {
+        n_cur = __ldg(order + li);
+        if (lane < (int)(sizeof(PlaneTab) / 16)) cp_async16(my_tabs + lane * 4, reinterpret_cast<const float*>(ptab + n_cur) + lane * 4);
+        cp_async_commit();
+        if (li + gstride < list_hi) n_next = __ldg(order + li + gstride);
+    }
+    int it = 0;
     while (li < list_hi) {
-        RawLattice nxt;
         const int lnext = li + gstride;
-        if (lnext < list_hi) load_raw(nxt, tab, order, lnext);
+        const float* tb = my_tabs + (it & 1) * TABF;
+        cp_async_wait<0>();
+        __syncwarp();
+        // prefetch the next RoI's table into the other buffer, and the index after that
+        int n_next2 = 0;
+        if (lnext < list_hi) {
+            if (lane < (int)(sizeof(PlaneTab) / 16))
+                cp_async16(my_tabs + ((it + 1) & 1) * TABF + lane * 4, reinterpret_cast<const float*>(ptab + n_next) + lane * 4);
+            if (lnext + gstride < list_hi) n_next2 = __ldg(order + lnext + gstride);
+        }
+        cp_async_commit();
 
-        // per-lane tables: column byte offset / x weight per lattice column, row byte offset / y weights per row
-        int xoff[G], yoff[G];
-        float wxl[G], wy0[G], wy1[G];
-        {
-            const unsigned vy = (unsigned)cur.tail.y, vx = (unsigned)cur.tail.z;
+        const PlaneTab* t = reinterpret_cast<const PlaneTab*>(tb);
+        unsigned xaddr[G];
+        float wx[G];
 #pragma unroll
-            for (int p = 0; p < G; ++p) {
-                float xf = __int_as_float(pick(cur.xf, p)), yf = __int_as_float(pick(cur.yf, p));
-                bool okx = (vx >> p) & 1u, oky = (vy >> p) & 1u;
-                xoff[p] = pick(cur.xs, p) * (kPlaneK * (int)sizeof(float));
-                float wx = dx ? xf : 1.f - xf;
-                if (POOL == I2V_POOL_AVG) wx *= 0.25f;  // the pool's divide, folded into the column weight
-                wxl[p] = okx ? wx : 0.f;
-                yoff[p] = pick(cur.ys, p) * row_bytes;
-                wy0[p] = oky ? 1.f - yf : 0.f;
-                wy1[p] = oky ? yf : 0.f;
-            }
+        for (int p = 0; p < G; ++p) {
+            xaddr[p] = lane_base + (unsigned)t->xoff[p];
+            wx[p] = dx ? t->wxr[p] : t->wxl[p];
         }
         float part[NOUT];  // AVG: this half-warp's partial sums; MAX / NONE: the finished values
         float prev[G];
 #pragma unroll
         for (int ph = 0; ph < G; ++ph) {
+            const unsigned yoff = (unsigned)t->yoff[ph];
+            const float wy0 = t->wy0[ph], wy1 = t->wy1[ph];
             float curv[G];
 #pragma unroll
             for (int pw = 0; pw < G; ++pw) {
-                const char* a = pl0 + (yoff[ph] + xoff[pw]);
-                float f0 = *reinterpret_cast<const float*>(a);
-                float f1 = *reinterpret_cast<const float*>(a + (WT ? WT * kPlaneK * 4 : row_bytes));
-                curv[pw] = (f0 * wy0[ph] + f1 * wy1[ph]) * wxl[pw];
+                const unsigned a = xaddr[pw] + yoff;
+                float f0, f1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f0) : "r"(a));
+                if (WT) {
+                    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(f1) : "r"(a), "n"(WT * kPlaneK * 4));
+                } else {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f1) : "r"(a + row_bytes));
+                }
+                curv[pw] = (f0 * wy0 + f1 * wy1) * wx[pw];
             }
             if (POOL != I2V_POOL_AVG) {
                 // max is not linear and NONE writes lattice values: combine the two columns now
@@ -380,10 +444,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
         }
 
         // ---- stage the [16][NOUT] tile and hand it to the TMA ----
-        float* st = my_stage + buf * TILE;
-        if (lane == 0) bulk_wait_read_1();  // the store that last read this buffer (two RoIs ago) is done
+        if (lane == 0) bulk_wait_read_all();  // the previous tile has left the staging buffer
         __syncwarp();
-        float* row = st + c * NOUT;
+        float* row = my_stage + c * NOUT;
         // outputs [0,16) are written by the low half-warp while the high one writes [16,32): 16 floats apart, so
         // the two halves use disjoint banks; the rest is written by the low half alone.
 #pragma unroll
@@ -410,17 +473,232 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0)
-            bulk_store_commit(out + ((size_t)cur.n * C + (size_t)ct * kPlaneK) * NOUT, st, TILE * sizeof(float));
-        buf ^= 1;
-        cur = nxt;
+            bulk_store_commit(out + ((size_t)n_cur * C + (size_t)ct * kPlaneK) * NOUT, my_stage, TILE * sizeof(float));
+        n_cur = n_next;
+        n_next = n_next2;
         li = lnext;
+        ++it;
     }
     if (lane == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------ plane backward
+// One CTA per (frame, 16 channels) OWNS those 16 gradient planes: they are accumulated in shared memory and written
+// to HBM exactly once, so there is no global atomic, no pre-zeroing pass and the result is deterministic.
+// Inside the CTA every consumer warp owns 4 of the planes; its 32 lanes are (channel 0-3) x (lattice row 0-7) and
+// walk the frame's RoIs in list order.  For one RoI a lane forms its row of lattice gradients (the pool's backward
+// is two adds), weights it per column, and adds it to the two feature rows it touches with plain
+// load / fma / store -- no atomics are needed because
+//   * rows of different lattice rows are distinct cells unless the start cells repeat, and repeated start cells
+//     are serialised by their position in the run (y_runpos), one __syncwarp apart;
+//   * columns with a repeated start cell are merged in registers first (x_same);
+//   * the upper and lower feature row of a lattice row are written in two phases, one __syncwarp apart.
+// The pooled-gradient tiles ([16][P*P] floats, contiguous in NCHW) and the RoI tables stream in through a TMA bulk
+// copy ring fed by a producer warp, so HBM latency is hidden without occupancy.
+constexpr int kBwdK = 16;
+constexpr int kBwdConsumerWarps = 4;
+constexpr int kBwdThreads = (kBwdConsumerWarps + 1) * 32;
+constexpr int kBwdStages = 8;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+__host__ __device__ inline int bwd_plane_pitch(int HW) { return HW + ((8 - HW % 32) + 32) % 32; }  // == 8 (mod 32)
+
+template <int P, int POOL, int WT>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+    lattice_bwd_plane_kernel(const float* __restrict__ grad_out, const LatticeRoi* __restrict__ tab,
+                             const int* __restrict__ order, const int* __restrict__ starts,
+                             float* __restrict__ grad_in, int C, int H, int Wrt) {
+    constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
+    constexpr int NOUT = P * P;
+    constexpr int TILE_BYTES = kBwdK * NOUT * (int)sizeof(float);
+    constexpr int STAGE_BYTES = TILE_BYTES + (int)sizeof(LatticeRoi);
+    static_assert(G <= 8 && TILE_BYTES % 16 == 0 && sizeof(LatticeRoi) % 16 == 0, "stage layout");
+    extern __shared__ __align__(128) unsigned char bsmem[];
+    const int W = WT ? WT : Wrt;
+    const int HW = H * W;
+    const int HWp = bwd_plane_pitch(HW);
+    unsigned char* ring = bsmem;                                                     // [stages][STAGE_BYTES]
+    uint64_t* full = reinterpret_cast<uint64_t*>(bsmem + kBwdStages * STAGE_BYTES);  // [stages]
+    uint64_t* empty = full + kBwdStages;                                             // [stages]
+    float* planes = reinterpret_cast<float*>(empty + kBwdStages);                    // [16][HWp]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctiles = C / kBwdK;
+    const int ct = blockIdx.x % ctiles;
+    const int b = blockIdx.x / ctiles;
+    const int list_lo = __ldg(starts + b), list_hi = __ldg(starts + b + 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < kBwdStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kBwdConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kBwdK * HWp; i += kBwdThreads) planes[i] = 0.f;
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == kBwdConsumerWarps) {
+        // ---- producer: one thread keeps the ring full ----
+        if (lane == 0) {
+            int it = 0;
+            for (int li = list_lo; li < list_hi; ++li, ++it) {
+                const int s = it % kBwdStages;
+                if (it >= kBwdStages) mbar_wait(empty + s, ((it / kBwdStages) - 1) & 1);
+                const int n = __ldg(order + li);
+                unsigned char* dst = ring + s * STAGE_BYTES;
+                mbar_expect_tx(full + s, STAGE_BYTES);
+                bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, full + s);
+                bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(LatticeRoi), full + s);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    const int cl = lane >> 3, ph = lane & 7;
+    const int c = warp * 4 + cl;
+    float* plane = planes + (size_t)c * HWp;
+    int it = 0;
+    for (int li = list_lo; li < list_hi; ++li, ++it) {
+        const int s = it % kBwdStages;
+        mbar_wait(full + s, (it / kBwdStages) & 1);
+        const float* tile = reinterpret_cast<const float*>(ring + s * STAGE_BYTES);
+        const LatticeRoi* t = reinterpret_cast<const LatticeRoi*>(ring + s * STAGE_BYTES + TILE_BYTES);
+
+        const unsigned vx = t->valid_x, vy = t->valid_y, xsame = t->x_same;
+        const int maxrun = (int)t->y_maxrun;
+        const unsigned ax = vx & ~xsame & ((1u << G) - 1u);  // columns that still own a pair of cells after merging
+        if (maxrun > 0 && ax != 0u) {
+            // uniform column tables
+            int xs[G];
+            float wx0[G], wx1[G];
+            {
+                const int4* qs = reinterpret_cast<const int4*>(t->x.start);
+                const float4* qf = reinterpret_cast<const float4*>(t->x.frac);
+                int4 s0 = qs[0], s1 = qs[1];
+                float4 f0 = qf[0], f1 = qf[1];
+                const int si[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float fi[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                const float q = (POOL == I2V_POOL_AVG) ? 0.25f : 1.f;
+#pragma unroll
+                for (int p = 0; p < G; ++p) {
+                    bool ok = (vx >> p) & 1u;
+                    xs[p] = si[p];
+                    wx0[p] = ok ? (1.f - fi[p]) * q : 0.f;
+                    wx1[p] = ok ? fi[p] * q : 0.f;
+                }
+            }
+            // this lane's lattice row
+            const bool oky = (ph < G) && ((vy >> ph) & 1u);
+            const int ys = t->y.start[ph & (kMaxLattice - 1)];
+            const float yf = t->y.frac[ph & (kMaxLattice - 1)];
+            const int myrun = (int)((t->y_runpos >> (4 * ph)) & 15u);
+            float gl[G];
+            if (POOL == I2V_POOL_NONE) {
+#pragma unroll
+                for (int pw = 0; pw < G; ++pw) gl[pw] = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + pw] : 0.f;
+            } else {
+                // pool backward: lattice point (ph,pw) collects the pooled cells (ph-1..ph, pw-1..pw)
+                float own[P], up[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    own[j] = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + j] : 0.f;
+                    up[j] = (ph >= 1) ? tile[c * NOUT + max(ph - 1, 0) * P + j] : 0.f;
+                }
+#pragma unroll
+                for (int pw = 0; pw < G; ++pw) {
+                    float v = 0.f;
+                    if (pw >= 1) v += own[pw - 1] + up[pw - 1];
+                    if (pw < P) v += own[pw] + up[pw];
+                    gl[pw] = v;
+                }
+            }
+            float t0[G], t1[G];
+#pragma unroll
+            for (int pw = 0; pw < G; ++pw) {
+                t0[pw] = gl[pw] * wx0[pw];
+                t1[pw] = gl[pw] * wx1[pw];
+            }
+            if (xsame != 0u) {  // merge columns that share their start cell into the first of the run
+#pragma unroll
+                for (int pw = G - 2; pw >= 0; --pw) {
+                    if ((xsame >> (pw + 1)) & 1u) {
+                        t0[pw] += t0[pw + 1];
+                        t1[pw] += t1[pw + 1];
+                    }
+                }
+            }
+            const float wy0 = 1.f - yf, wy1 = yf;
+            float* row0 = plane + ys * W;
+            for (int k = 0; k < maxrun; ++k) {
+                const bool act = oky && (myrun == k);
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy) {
+                    float* row = row0 + (dy ? W : 0);
+                    const float wy = dy ? wy1 : wy0;
+#pragma unroll
+                    for (int dxx = 0; dxx < 2; ++dxx) {
+                        float old[G];
+#pragma unroll
+                        for (int pw = 0; pw < G; ++pw)
+                            if (act && ((ax >> pw) & 1u)) old[pw] = row[xs[pw] + dxx];
+#pragma unroll
+                        for (int pw = 0; pw < G; ++pw)
+                            if (act && ((ax >> pw) & 1u)) row[xs[pw] + dxx] = old[pw] + (dxx ? t1[pw] : t0[pw]) * wy;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // ---- write this warp's four planes: the only write of these gradient bytes ----
+    __syncwarp();
+    float* dst = grad_in + ((size_t)b * C + (size_t)ct * kBwdK + (size_t)warp * 4) * HW;
+    for (int q = 0; q < 4; ++q) {
+        const float* src = planes + (size_t)(warp * 4 + q) * HWp;
+        for (int i = lane; i < HW; i += 32) dst[(size_t)q * HW + i] = src[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 struct LatticeWs {
     LatticeRoi* tab;
+    PlaneTab* ptab;
     int* roi_batch;
     int* counts;
     int* starts;
@@ -438,17 +716,20 @@ static LatticeWs carve_lattice_ws(void* ws, int batch, int num_rois, bool lists 
         w.counts = cv.take<int>((size_t)batch + 2);
         w.starts = cv.take<int>((size_t)batch + 2);
         w.order = cv.take<int>((size_t)num_rois);
+        w.ptab = cv.take<PlaneTab>((size_t)num_rois);
     }
     w.bytes = cv.used();
     return w;
 }
 
 static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W, int GH, int GW, float scale,
-                        const LatticeWs& w, bool lists, cudaStream_t stream) {
+                        const LatticeWs& w, bool lists, cudaStream_t stream, float ptab_scale = 0.f) {
     if (lists) I2V_CUDA_TRY(cudaMemsetAsync(w.counts, 0, sizeof(int) * ((size_t)batch + 2), stream));
     lattice_prep_kernel<<<ceil_div(num_rois, 128), 128, 0, stream>>>(rois, num_rois, batch, H, W, GH, GW, scale, w.tab,
                                                                      lists ? w.roi_batch : nullptr,
-                                                                     lists ? w.counts : nullptr);
+                                                                     lists ? w.counts : nullptr,
+                                                                     (lists && ptab_scale != 0.f) ? w.ptab : nullptr,
+                                                                     ptab_scale);
     I2V_TRY(check_launch("lattice_prep_kernel"));
     if (lists) {
         roi_bucket_kernel<<<batch + 1, 256, 0, stream>>>(w.roi_batch, num_rois, batch + 1, w.counts, w.starts, w.order);
@@ -458,9 +739,9 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
 }
 
 static size_t plane_fwd_smem_bytes(int H, int W, int P) {
-    size_t stage = (size_t)kPlaneWarps * 2 * kPlaneK * P * P;
-    size_t scratch = (size_t)kPlaneK * kFillPitch;
-    return ((size_t)H * W * kPlaneK + (stage > scratch ? stage : scratch)) * sizeof(float);
+    size_t stage = (size_t)kPlaneWarps * kPlaneK * P * P;
+    static_assert((size_t)kPlaneWarps * kPlaneK * 49 >= 2 * (size_t)kPlaneK * kFillPitch, "fill scratch fits the stage");
+    return ((size_t)H * W * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 2 * sizeof(PlaneTab);
 }
 
 static bool plane_forward_ok(const float* out, int batch, int C, int H, int W, int PH, int PW) {
@@ -482,10 +763,36 @@ static int launch_plane_fwd_w(const float* feat, const LatticeWs& w, float* out,
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctiles = C / kPlaneK;
     int split = plane_split(batch * ctiles);
-    kern<<<(batch + 1) * ctiles * split, kPlaneThreads, smem, stream>>>(feat, w.tab, w.order, w.starts, out, batch, C,
+    kern<<<(batch + 1) * ctiles * split, kPlaneThreads, smem, stream>>>(feat, w.ptab, w.order, w.starts, out, batch, C,
                                                                        H, W, split);
     return check_launch("lattice_fwd_plane_kernel");
 }
+static size_t plane_bwd_smem_bytes(int H, int W, int P) {
+    return (size_t)kBwdStages * ((size_t)kBwdK * P * P * sizeof(float) + sizeof(LatticeRoi)) +
+           2 * kBwdStages * sizeof(uint64_t) + (size_t)kBwdK * bwd_plane_pitch(H * W) * sizeof(float);
+}
+
+static bool plane_backward_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode) {
+    return batch > 0 && PH == 7 && PW == 7 && pool_mode != I2V_POOL_MAX && C % kBwdK == 0 && H >= 2 && W >= 2 &&
+           plane_bwd_smem_bytes(H, W, 7) <= (size_t)kMaxSmemPerCta && ((uintptr_t)grad_out & 15) == 0;
+}
+
+template <int POOL, int WT>
+static int launch_plane_bwd_w(const float* grad_out, const LatticeWs& w, float* grad_in, int batch, int C, int H, int W,
+                              cudaStream_t stream) {
+    auto kern = lattice_bwd_plane_kernel<7, POOL, WT>;
+    size_t smem = plane_bwd_smem_bytes(H, W, 7);
+    I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<batch * (C / kBwdK), kBwdThreads, smem, stream>>>(grad_out, w.tab, w.order, w.starts, grad_in, C, H, W);
+    return check_launch("lattice_bwd_plane_kernel");
+}
+template <int POOL>
+static int launch_plane_bwd(const float* grad_out, const LatticeWs& w, float* grad_in, int batch, int C, int H, int W,
+                            cudaStream_t stream) {
+    if (W == 63) return launch_plane_bwd_w<POOL, 63>(grad_out, w, grad_in, batch, C, H, W, stream);
+    return launch_plane_bwd_w<POOL, 0>(grad_out, w, grad_in, batch, C, H, W, stream);
+}
+
 template <int POOL>
 static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
                             cudaStream_t stream) {
@@ -546,7 +853,8 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
     }
     bool plane = can_plane && impl != I2V_IMPL_GATHER;
     I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, plane, w));
-    I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, plane, stream));
+    I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, plane, stream,
+                         pool_mode == I2V_POOL_AVG ? 0.25f : 1.f));
     if (plane) {
         if (pool_mode == I2V_POOL_AVG) return launch_plane_fwd<I2V_POOL_AVG>(features, w, out, batch, channels, height, width, stream);
         if (pool_mode == I2V_POOL_MAX) return launch_plane_fwd<I2V_POOL_MAX>(features, w, out, batch, channels, height, width, stream);
@@ -575,9 +883,19 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
     size_t in_elems = (size_t)batch * channels * height * width;
     if (in_elems == 0) return I2V_OK;
     I2V_REQUIRE(grad_in, "roi_align_backward: null grad_in");
-    if (impl == I2V_IMPL_PLANE) {
-        set_error("roi_align_backward: no plane kernel for this shape");
+    // the plane kernel overwrites grad_in, so it cannot serve the accumulate-into-caller's-buffer launcher
+    bool can_plane = zero_first && num_rois > 0 &&
+                     plane_backward_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    if (impl == I2V_IMPL_PLANE && !can_plane) {
+        set_error("roi_align_backward: the plane kernel needs a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
+                  "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
+    }
+    if (can_plane && impl != I2V_IMPL_GATHER) {
+        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        if (pool_mode == I2V_POOL_AVG) return launch_plane_bwd<I2V_POOL_AVG>(grad_out, w, grad_in, batch, channels, height, width, stream);
+        return launch_plane_bwd<I2V_POOL_NONE>(grad_out, w, grad_in, batch, channels, height, width, stream);
     }
     if (zero_first) I2V_CUDA_TRY(cudaMemsetAsync(grad_in, 0, in_elems * sizeof(float), stream));
     if (num_rois == 0 || channels == 0) return I2V_OK;

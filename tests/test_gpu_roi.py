@@ -95,9 +95,11 @@ def test_roi_align_empty(ops):
 
 
 @pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "auto"])
+@pytest.mark.parametrize("impl", ["gather", "plane", "auto"])
 @pytest.mark.parametrize("case", CASES)
 def test_roi_align_backward(ops, orc, case, impl, pool):
+    if impl == "plane" and pool == "max":
+        pytest.skip("the max pool's arg-max routing needs the features: gather kernel only")
     B, C, H, W, N = case
     feat = synth.feature_map(100 + B, B, C, H, W)
     rois = synth.rois(200 + N, N, batch=B)
@@ -107,6 +109,46 @@ def test_roi_align_backward(ops, orc, case, impl, pool):
     want = orc.roi_align_pooled_backward(g, feat, rois, 7, 7, SCALE, pool, nthreads=8)
     got = ops.roi_align_backward(cuda(g), cuda(feat), cuda(rois), feat.shape, 7, 7, SCALE, pool, impl)
     close(got, want)
+
+
+def test_roi_align_backward_small_and_repeated_cells(ops, orc):
+    # tiny RoIs (several lattice points per cell in both axes), RoIs hugging the borders and many RoIs stacked on the
+    # same cells: exercises the run-position serialisation and the column merge of the plane kernel
+    rng = np.random.default_rng(17)
+    B, C, H, W, N = 2, 16, 38, 63, 120
+    feat_shape = (B, C, H, W)
+    x1 = rng.uniform(0, 980, N); y1 = rng.uniform(0, 580, N)
+    w = rng.choice([2.0, 9.0, 20.0, 45.0, 70.0, 130.0], N); h = rng.choice([2.0, 9.0, 20.0, 45.0, 70.0, 130.0], N)
+    rois = np.stack([rng.integers(0, B, N), x1, y1, np.minimum(x1 + w, 999), np.minimum(y1 + h, 599)], 1).astype(np.float32)
+    rois[:10] = rois[0]                     # identical RoIs
+    rois[10:14] = [[0, 0, 0, 999, 599], [1, 990, 590, 999, 599], [0, 0, 560, 30, 599], [1, 960, 0, 999, 20]]
+    g = rng.standard_normal((N, C, 7, 7)).astype(np.float32)
+    for pool in ("avg", "none"):
+        want = orc.roi_align_pooled_backward(g, None if pool != "max" else None, rois, 7, 7, SCALE, pool) \
+            if False else orc.roi_align_pooled_backward(g, np.zeros(feat_shape, np.float32), rois, 7, 7, SCALE, pool)
+        got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, "plane")
+        close(got, want)
+        again = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, "plane")
+        assert torch.equal(got, again)      # no atomics: bit-reproducible
+
+
+def test_roi_align_backward_frames_without_rois_are_zeroed(ops, orc):
+    B, C, H, W = 3, 16, 38, 63
+    rois = synth.rois(5, 20, batch=1)       # every RoI in frame 0
+    g = np.random.default_rng(2).standard_normal((20, C, 7, 7)).astype(np.float32)
+    gin = torch.full((B, C, H, W), 3.0, device="cuda")
+    from i2vsgg_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    r, gg = cuda(rois), cuda(g)
+    ws = torch.empty(lib.i2v_roi_align_workspace_bytes(B, 20), dtype=torch.uint8, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.i2v_roi_align_backward(P(gg), None, P(r), P(gin), B, C, H, W, 20, 7, 7, SCALE, 1, 2, P(ws), ws.numel(),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    want = orc.roi_align_pooled_backward(g, np.zeros((B, C, H, W), np.float32), rois, 7, 7, SCALE, "avg")
+    close(gin, want)
+    assert float(gin[1:].abs().max()) == 0.0
 
 
 def test_roi_align_autograd_module(ops, orc):
