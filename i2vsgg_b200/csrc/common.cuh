@@ -110,14 +110,12 @@ struct alignas(16) LatticeRoi {
 };
 
 // What the forward plane kernel needs of one RoI (lattices of up to 8 points per axis): byte offsets into the
-// [cell][16 channels] shared-memory planes and weights with validity (and the avg pool's 1/4) already folded in.
+// [row][64 columns][16 channels] shared-memory planes and weights with validity (and the avg pool's 1/4) folded in.
+// A bilinear sample reads two horizontally adjacent cells; xa lists them even column first, xb odd column first.
 struct alignas(16) PlaneTab {
-    int xoff[8];    // start column * 64 bytes
-    float wxl[8];   // weight of the left cell  (1 - frac) * scale, 0 for an out-of-range lattice column
-    float wxr[8];   // weight of the right cell  frac * scale
-    int yoff[8];    // start row * W * 64 bytes
-    float wy0[8];   // weight of the upper row (1 - frac), 0 for an out-of-range lattice row
-    float wy1[8];   // weight of the lower row  frac
+    float4 xa[8];  // {byte offset of the even-column cell (int bits), its weight, offset of the odd-column cell, its weight}
+    float4 xb[8];  // the same pair in the opposite order
+    float4 y[8];   // {byte offset of the upper row (int bits), weight of the upper row, weight of the lower row, 0}
 };
 
 }  // namespace i2v

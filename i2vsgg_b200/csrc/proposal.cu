@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) proposal_decode_kernel(const float* __res
 // ------------------------------------------------------------------------------------------ segmented sort
 constexpr int kSortThreads = 1024;
 constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortBatch = 8;  // groups of 32 keys in flight per warp
 
 // Monotone map float -> uint32 whose ASCENDING order is the DESCENDING order of the floats.
 __device__ __forceinline__ unsigned desc_key(float f) {
@@ -107,15 +108,24 @@ __global__ void __launch_bounds__(kSortThreads) segment_sort_kernel(const float*
         unsigned* dst_i = (pass & 1) ? i1 : i0;
         for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&hist[0][0])[i] = 0;
         __syncthreads();
-        // sweep 1: warp-private digit counts
-        for (int b = lo; b < hi; b += 32) {
-            int i = b + lane;
-            bool ok = i < hi;
-            unsigned key = ok ? (pass == 0 ? desc_key(kin[(size_t)i * key_stride]) : src_k[i]) : 0u;
-            unsigned d = ok ? ((key >> shift) & 255u) : (256u + lane);
-            unsigned peers = __match_any_sync(0xffffffffu, d);
-            if (ok && lane == (__ffs(peers) - 1)) hist[warp][d] += __popc(peers);
-            __syncwarp();
+        // sweep 1: warp-private digit counts.  Eight groups of 32 keys are fetched at once so that the global-memory
+        // latency is paid once per 256 keys, not once per group.
+        for (int b0 = lo; b0 < hi; b0 += 32 * kSortBatch) {
+            unsigned keyv[kSortBatch];
+#pragma unroll
+            for (int q = 0; q < kSortBatch; ++q) {
+                int i = b0 + q * 32 + lane;
+                keyv[q] = (i < hi) ? (pass == 0 ? desc_key(kin[(size_t)i * key_stride]) : src_k[i]) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < kSortBatch; ++q) {
+                if (b0 + q * 32 >= hi) break;
+                bool ok = b0 + q * 32 + lane < hi;
+                unsigned d = ok ? ((keyv[q] >> shift) & 255u) : (256u + lane);
+                unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (ok && lane == (__ffs(peers) - 1)) hist[warp][d] += __popc(peers);
+                __syncwarp();
+            }
         }
         __syncthreads();
         // offsets: digit-major, then warp
@@ -154,25 +164,34 @@ __global__ void __launch_bounds__(kSortThreads) segment_sort_kernel(const float*
             }
         }
         __syncthreads();
-        // sweep 2: stable scatter
-        for (int b = lo; b < hi; b += 32) {
-            int i = b + lane;
-            bool ok = i < hi;
-            unsigned key = ok ? (pass == 0 ? desc_key(kin[(size_t)i * key_stride]) : src_k[i]) : 0u;
-            unsigned idx = ok ? (pass == 0 ? (unsigned)i : src_i[i]) : 0u;
-            unsigned d = ok ? ((key >> shift) & 255u) : (256u + lane);
-            unsigned peers = __match_any_sync(0xffffffffu, d);
-            unsigned pos = 0;
-            if (ok) pos = hist[warp][d] + __popc(peers & ((1u << lane) - 1u));
-            __syncwarp();
-            if (ok && lane == (__ffs(peers) - 1)) hist[warp][d] += __popc(peers);
-            __syncwarp();
-            if (ok) {
-                if (pass == 3) {
-                    out[pos] = (int)idx;
-                } else {
-                    dst_k[pos] = key;
-                    dst_i[pos] = idx;
+        // sweep 2: stable scatter (same batching)
+        for (int b0 = lo; b0 < hi; b0 += 32 * kSortBatch) {
+            unsigned keyv[kSortBatch], idxv[kSortBatch];
+#pragma unroll
+            for (int q = 0; q < kSortBatch; ++q) {
+                int i = b0 + q * 32 + lane;
+                bool ok = i < hi;
+                keyv[q] = ok ? (pass == 0 ? desc_key(kin[(size_t)i * key_stride]) : src_k[i]) : 0u;
+                idxv[q] = ok ? (pass == 0 ? (unsigned)i : src_i[i]) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < kSortBatch; ++q) {
+                if (b0 + q * 32 >= hi) break;
+                bool ok = b0 + q * 32 + lane < hi;
+                unsigned d = ok ? ((keyv[q] >> shift) & 255u) : (256u + lane);
+                unsigned peers = __match_any_sync(0xffffffffu, d);
+                unsigned pos = 0;
+                if (ok) pos = hist[warp][d] + __popc(peers & ((1u << lane) - 1u));
+                __syncwarp();
+                if (ok && lane == (__ffs(peers) - 1)) hist[warp][d] += __popc(peers);
+                __syncwarp();
+                if (ok) {
+                    if (pass == 3) {
+                        out[pos] = (int)idxv[q];
+                    } else {
+                        dst_k[pos] = keyv[q];
+                        dst_i[pos] = idxv[q];
+                    }
                 }
             }
         }

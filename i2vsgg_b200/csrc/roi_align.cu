@@ -87,17 +87,19 @@ __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois
         t.pad_ = 0;
     }
     tab[n] = t;
-    if (ptab) {  // the forward plane kernel's view: byte offsets into the [cell][16] planes and ready-to-use weights
+    if (ptab) {  // the forward plane kernel's view: byte offsets into the [row][64][16] planes, ready-to-use weights
         PlaneTab q;
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             bool okx = (t.valid_x >> p) & 1u, oky = (t.valid_y >> p) & 1u;
-            q.xoff[p] = t.x.start[p] * (16 * 4);
-            q.wxl[p] = okx ? (1.f - t.x.frac[p]) * ptab_scale : 0.f;
-            q.wxr[p] = okx ? t.x.frac[p] * ptab_scale : 0.f;
-            q.yoff[p] = t.y.start[p] * W * (16 * 4);
-            q.wy0[p] = oky ? 1.f - t.y.frac[p] : 0.f;
-            q.wy1[p] = oky ? t.y.frac[p] : 0.f;
+            int sx = t.x.start[p];
+            float wl = okx ? (1.f - t.x.frac[p]) * ptab_scale : 0.f, wr = okx ? t.x.frac[p] * ptab_scale : 0.f;
+            int even = (sx & 1) ? sx + 1 : sx, odd = (sx & 1) ? sx : sx + 1;
+            float we = (sx & 1) ? wr : wl, wo = (sx & 1) ? wl : wr;
+            q.xa[p] = make_float4(__int_as_float(even * 64), we, __int_as_float(odd * 64), wo);
+            q.xb[p] = make_float4(__int_as_float(odd * 64), wo, __int_as_float(even * 64), we);
+            q.y[p] = make_float4(__int_as_float(t.y.start[p] * 4096), oky ? 1.f - t.y.frac[p] : 0.f,
+                                 oky ? t.y.frac[p] : 0.f, 0.f);
         }
         ptab[n] = q;
     }
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(256) lattice_bwd_gather_kernel(const float* __
 
 // ------------------------------------------------------------------------------------------ plane forward
 constexpr int kPlaneK = 16;        // channels per CTA
-constexpr int kPlaneWarps = 16;    // warps per CTA
+constexpr int kPlaneWarps = 9;     // warps per CTA (each works on two RoIs at a time)
 constexpr int kPlaneThreads = kPlaneWarps * 32;
 constexpr int kFillCells = 384;    // cells per fill round
 constexpr int kFillPitch = 386;    // == 2 (mod 32): the transposing read of a round is bank-conflict free
@@ -288,27 +290,33 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// P = pooled size (output is P x P); lattice G = P (+1 when a pool follows); WT = compile-time map width (0: runtime).
-// A warp works on one RoI x 16 channels at a time: lanes 0-15 read the left cell of every bilinear pair, lanes
-// 16-31 the right one (adjacent 64-byte rows of the [cell][16] layout: 32 distinct banks), each half carries the
-// partial sums of its column, the halves are combined with one shuffle per output and the finished
-// [16][P*P] tile -- which is contiguous in the NCHW output -- leaves through a TMA bulk store.
-template <int P, int POOL, int WT>
+// P = pooled size (output is P x P); lattice G = P (+1 when a pool follows).
+// Shared-memory planes: [row][64 columns][16 channels] fp32 (row pitch padded to 64 cells, so the parity of a cell is
+// the parity of its column).  Lanes are channels: a warp works on TWO RoIs x 16 channels at a time, lanes 0-15 on one
+// RoI and lanes 16-31 on another.  Of the two horizontally adjacent cells of a bilinear sample the low half-warp
+// always reads the even-column cell first and the high half-warp the odd-column cell first (the prep kernel stores
+// both orders), so the two halves hit disjoint bank groups in every load: conflict free by construction, and all
+// index math is uniform per half-warp.  Each lane ends up with the P*P outputs of its (RoI, channel); they are staged
+// as [16][P*P] -- contiguous in the NCHW output -- and leave through a TMA bulk store per half.
+constexpr int kPitch = 64;                      // cells per shared-memory row
+constexpr int kCellBytes = kPlaneK * 4;         // 64 bytes per cell
+constexpr int kRowBytes = kPitch * kCellBytes;  // 4096 bytes per row
+
+template <int P, int POOL>
 __global__ void __launch_bounds__(kPlaneThreads, 1)
     lattice_fwd_plane_kernel(const float* __restrict__ feat, const PlaneTab* __restrict__ ptab,
                              const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ out,
-                             int batch, int C, int H, int Wrt, int split) {
+                             int batch, int C, int H, int W, int split) {
     constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
     constexpr int NOUT = P * P;
     constexpr int TILE = kPlaneK * NOUT;  // floats per staged output tile
     constexpr int TABF = (int)(sizeof(PlaneTab) / sizeof(float));
+    constexpr int TABV = (int)(sizeof(PlaneTab) / 16);
     static_assert(G <= 8, "tables hold 8 lattice points per axis");
     extern __shared__ __align__(128) float smem[];
-    const int W = WT ? WT : Wrt;
-    const int HW = H * W;
-    float* planes = smem;                            // [HW][16]
-    float* stage = smem + (size_t)HW * kPlaneK;      // [warps][TILE]; doubles as the fill scratch [2][16][386]
-    float* tabs = stage + (size_t)kPlaneWarps * TILE;  // [warps][2][sizeof(PlaneTab)]
+    float* planes = smem;                                    // [H][64][16]
+    float* stage = smem + (size_t)H * kPitch * kPlaneK;      // [warps][2][TILE]; doubles as the fill scratch
+    float* tabs = stage + (size_t)kPlaneWarps * 2 * TILE;    // [warps][2 halves][2 buffers][PlaneTab]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctiles = C / kPlaneK;
@@ -317,32 +325,48 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
     const int b = blockIdx.x / (split * ctiles);
     const int list_lo = __ldg(starts + b), list_hi = __ldg(starts + b + 1);
     if (list_lo == list_hi) return;
-    const int gwarp = s * kPlaneWarps + warp, gstride = split * kPlaneWarps;
+    const int role = lane >> 4, c = lane & 15;
+    const int ghalf = (s * kPlaneWarps + warp) * 2 + role, gstride = split * kPlaneWarps * 2;
 
     if (b == batch) {  // RoIs with an out-of-range batch index: zero rows
-        for (int li = list_lo + gwarp; li < list_hi; li += gstride) {
+        for (int li = list_lo + ghalf; li < list_hi; li += gstride) {
             float4* dst = reinterpret_cast<float4*>(out + ((size_t)__ldg(order + li) * C + (size_t)ct * kPlaneK) * NOUT);
-            for (int i = lane; i < TILE / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = c; i < TILE / 4; i += 16) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         return;
     }
 
-    // ---- fill: 16 planes, global [c][cell] -> shared [cell][16].  Rounds of 384 cells stream through a double
-    // buffered [16][386] scratch with cp.async, so the copy of round r+1 overlaps the transposition of round r ----
+    // ---- fill: 16 planes, global [c][row][col] -> shared [row][col][16].  Rounds of whole rows stream through a
+    // double buffered [16][386] scratch with cp.async: the copy of round r+1 overlaps the transposition of round r.
+    // Index math is per warp-wide item (64 cells of one plane / one pair of cells x 16 channels), not per element ----
     {
+        const int HW = H * W;
         const float* src = feat + ((size_t)b * C + (size_t)ct * kPlaneK) * HW;
-        const int rounds = ceil_div(HW, kFillCells);
+        const int rpr = kFillCells / W;  // rows per round
+        const int round_cells = rpr * W;
+        const int rounds = ceil_div(H, rpr);
+        const int nseg = ceil_div(round_cells, 64);
+        const bool pairs = ((HW | round_cells) & 1) == 0 && (((uintptr_t)feat & 7) == 0);  // 8-byte copies allowed
         auto issue = [&](int r) {
             float* scr = stage + (r & 1) * (kPlaneK * kFillPitch);
-            const int c0 = r * kFillCells;
-            const int ncell = min(kFillCells, HW - c0);
-            for (int i = tid; i < kPlaneK * kFillCells; i += kPlaneThreads) {
-                int c = i / kFillCells, x = i - c * kFillCells;
-                if (x < ncell) cp_async4(scr + c * kFillPitch + x, src + (size_t)c * HW + c0 + x);
+            const int c0 = r * round_cells;
+            const int ncell = min(round_cells, HW - c0);
+            for (int item = warp; item < kPlaneK * nseg; item += kPlaneWarps) {
+                const int cc = item / nseg, seg = item - cc * nseg;
+                const int x = seg * 64 + lane * 2;
+                const float* g = src + (size_t)cc * HW + c0 + x;
+                float* d = scr + cc * kFillPitch + x;
+                if (pairs) {
+                    if (x < ncell) cp_async8(d, g);
+                } else {
+                    if (x < ncell) cp_async4(d, g);
+                    if (x + 1 < ncell) cp_async4(d + 1, g + 1);
+                }
             }
             cp_async_commit();
         };
         issue(0);
+        const int tc = lane & 15, tdx = lane >> 4;
         for (int r = 0; r < rounds; ++r) {
             if (r + 1 < rounds) {
                 issue(r + 1);
@@ -351,85 +375,97 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
                 cp_async_wait<0>();
             }
             __syncthreads();
-            const float* scr = stage + (r & 1) * (kPlaneK * kFillPitch);
-            const int c0 = r * kFillCells;
-            const int ncell = min(kFillCells, HW - c0);
-            for (int i = tid; i < kPlaneK * kFillCells; i += kPlaneThreads) {
-                int c = i & (kPlaneK - 1), x = i >> 4;
-                if (x < ncell) planes[(size_t)(c0 + x) * kPlaneK + c] = scr[c * kFillPitch + x];
+            const float* scr = stage + (r & 1) * (kPlaneK * kFillPitch) + tc * kFillPitch;
+            const int row0 = r * rpr;
+            const int nrow = min(rpr, H - row0);
+            // one item = two adjacent cells of one row x 16 channels: conflict-free read, 128 contiguous bytes written
+            for (int item = warp; item < nrow * 32; item += kPlaneWarps) {
+                const int ry = item >> 5, rx = (item & 31) * 2 + tdx;
+                if (rx < W) planes[((size_t)(row0 + ry) * kPitch + rx) * kPlaneK + tc] = scr[ry * W + rx];
             }
             __syncthreads();
         }
     }
 
-    const int c = lane & 15, dx = lane >> 4;
-    // byte address (shared window) of this lane's channel in cell 0, row 0, already shifted to its column
-    const unsigned lane_base = (unsigned)__cvta_generic_to_shared(planes + c + dx * kPlaneK);
-    const int row_bytes = W * kPlaneK * (int)sizeof(float);
-    float* my_stage = stage + (size_t)warp * TILE;
-    float* my_tabs = tabs + (size_t)warp * 2 * TABF;
+    // shared-window byte address of this lane's channel in cell (0,0)
+    const unsigned lane_base = (unsigned)__cvta_generic_to_shared(planes + c);
+    float* my_stage = stage + ((size_t)warp * 2 + role) * TILE;
+    float* my_tabs = tabs + ((size_t)warp * 2 + role) * 2 * TABF;
 
-    int li = list_lo + gwarp;
+    int li = list_lo + ghalf;
     int n_cur = 0, n_next = 0;
+    auto fetch_table = [&](int n, int bufi) {  // 16 lanes copy the 24 x 16 bytes of one table
+        const float* g = reinterpret_cast<const float*>(ptab + n);
+        float* d = my_tabs + bufi * TABF;
+        cp_async16(d + c * 4, g + c * 4);
+        if (c + 16 < TABV) cp_async16(d + (c + 16) * 4, g + (c + 16) * 4);
+    };
     if (li < list_hi) {
         n_cur = __ldg(order + li);
-        if (lane < (int)(sizeof(PlaneTab) / 16)) cp_async16(my_tabs + lane * 4, reinterpret_cast<const float*>(ptab + n_cur) + lane * 4);
-        cp_async_commit();
+        fetch_table(n_cur, 0);
         if (li + gstride < list_hi) n_next = __ldg(order + li + gstride);
+    } else {
+        // this half never has work: a zero table keeps its lanes harmless
+        for (int i = c; i < 2 * TABF; i += 16) my_tabs[i] = 0.f;
     }
+    cp_async_commit();
     int it = 0;
-    while (li < list_hi) {
+    while (__any_sync(0xffffffffu, li < list_hi)) {
+        const bool active = li < list_hi;
         const int lnext = li + gstride;
-        const float* tb = my_tabs + (it & 1) * TABF;
         cp_async_wait<0>();
         __syncwarp();
+        const PlaneTab* t = reinterpret_cast<const PlaneTab*>(my_tabs + (it & 1) * TABF);
         // prefetch the next RoI's table into the other buffer, and the index after that
         int n_next2 = 0;
-        if (lnext < list_hi) {
-            if (lane < (int)(sizeof(PlaneTab) / 16))
-                cp_async16(my_tabs + ((it + 1) & 1) * TABF + lane * 4, reinterpret_cast<const float*>(ptab + n_next) + lane * 4);
-            if (lnext + gstride < list_hi) n_next2 = __ldg(order + lnext + gstride);
+        if (active) {
+            if (lnext < list_hi) {
+                fetch_table(n_next, (it + 1) & 1);
+                if (lnext + gstride < list_hi) n_next2 = __ldg(order + lnext + gstride);
+            } else {
+                float* d = my_tabs + ((it + 1) & 1) * TABF;  // the half runs dry after this RoI
+                for (int i = c; i < TABF; i += 16) d[i] = 0.f;
+            }
         }
         cp_async_commit();
 
-        const PlaneTab* t = reinterpret_cast<const PlaneTab*>(tb);
-        unsigned xaddr[G];
-        float wx[G];
+        unsigned xfirst[G], xsecond[G];
+        float wfirst[G], wsecond[G];
+        {
+            const float4* xe = role ? t->xb : t->xa;
 #pragma unroll
-        for (int p = 0; p < G; ++p) {
-            xaddr[p] = lane_base + (unsigned)t->xoff[p];
-            wx[p] = dx ? t->wxr[p] : t->wxl[p];
+            for (int p = 0; p < G; ++p) {
+                float4 e = xe[p];
+                xfirst[p] = (unsigned)__float_as_int(e.x);
+                wfirst[p] = e.y;
+                xsecond[p] = (unsigned)__float_as_int(e.z);
+                wsecond[p] = e.w;
+            }
         }
-        float part[NOUT];  // AVG: this half-warp's partial sums; MAX / NONE: the finished values
+        float part[NOUT];
         float prev[G];
 #pragma unroll
         for (int ph = 0; ph < G; ++ph) {
-            const unsigned yoff = (unsigned)t->yoff[ph];
-            const float wy0 = t->wy0[ph], wy1 = t->wy1[ph];
+            const float4 ye = t->y[ph];
+            const unsigned ybase = lane_base + (unsigned)__float_as_int(ye.x);
+            const float wy0 = ye.y, wy1 = ye.z;
             float curv[G];
 #pragma unroll
             for (int pw = 0; pw < G; ++pw) {
-                const unsigned a = xaddr[pw] + yoff;
-                float f0, f1;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f0) : "r"(a));
-                if (WT) {
-                    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(f1) : "r"(a), "n"(WT * kPlaneK * 4));
-                } else {
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f1) : "r"(a + row_bytes));
-                }
-                curv[pw] = (f0 * wy0 + f1 * wy1) * wx[pw];
-            }
-            if (POOL != I2V_POOL_AVG) {
-                // max is not linear and NONE writes lattice values: combine the two columns now
-#pragma unroll
-                for (int pw = 0; pw < G; ++pw) curv[pw] += __shfl_xor_sync(0xffffffffu, curv[pw], 16);
+                const unsigned a = ybase + xfirst[pw], bb = ybase + xsecond[pw];
+                float a0, a1, b0, b1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(a));
+                asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(a1) : "r"(a), "n"(kRowBytes));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b0) : "r"(bb));
+                asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(b1) : "r"(bb), "n"(kRowBytes));
+                curv[pw] = (a0 * wy0 + a1 * wy1) * wfirst[pw] + (b0 * wy0 + b1 * wy1) * wsecond[pw];
             }
             if (POOL == I2V_POOL_NONE) {
 #pragma unroll
                 for (int pw = 0; pw < G; ++pw) part[ph * P + pw] = curv[pw];
             } else if (POOL == I2V_POOL_AVG) {
 #pragma unroll
-                for (int pw = 0; pw < P; ++pw) curv[pw] += curv[pw + 1];  // row sums of adjacent columns
+                for (int pw = 0; pw < P; ++pw) curv[pw] += curv[pw + 1];  // row sums of adjacent columns (x 1/4 in wx)
                 if (ph > 0) {
 #pragma unroll
                     for (int pw = 0; pw < P; ++pw) part[(ph - 1) * P + pw] = prev[pw] + curv[pw];
@@ -443,43 +479,22 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
             for (int pw = 0; pw < G; ++pw) prev[pw] = curv[pw];
         }
 
-        // ---- stage the [16][NOUT] tile and hand it to the TMA ----
-        if (lane == 0) bulk_wait_read_all();  // the previous tile has left the staging buffer
+        // ---- stage the [16][NOUT] tile of this half and hand it to the TMA ----
+        if (c == 0) bulk_wait_read_all();  // the previous tile of this half has left the staging buffer
         __syncwarp();
-        float* row = my_stage + c * NOUT;
-        // outputs [0,16) are written by the low half-warp while the high one writes [16,32): 16 floats apart, so
-        // the two halves use disjoint banks; the rest is written by the low half alone.
+        float* row = my_stage + c * NOUT;   // the two halves' tiles are 16 banks apart: conflict free
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if (k + 16 < NOUT) {
-                float mine = dx ? part[k + 16] : part[k];
-                if (POOL == I2V_POOL_AVG) {
-                    float send = dx ? part[k] : part[k + 16];
-                    mine += __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-                row[k + dx * 16] = mine;
-            } else if (k < NOUT) {
-                float mine = part[k];
-                if (POOL == I2V_POOL_AVG) mine += __shfl_xor_sync(0xffffffffu, mine, 16);
-                if (!dx) row[k] = mine;
-            }
-        }
-#pragma unroll
-        for (int k = 32; k < NOUT; ++k) {
-            float mine = part[k];
-            if (POOL == I2V_POOL_AVG) mine += __shfl_xor_sync(0xffffffffu, mine, 16);
-            if (!dx) row[k] = mine;
-        }
+        for (int k = 0; k < NOUT; ++k) row[k] = part[k];
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0)
+        if (c == 0 && active)
             bulk_store_commit(out + ((size_t)n_cur * C + (size_t)ct * kPlaneK) * NOUT, my_stage, TILE * sizeof(float));
         n_cur = n_next;
         n_next = n_next2;
         li = lnext;
         ++it;
     }
-    if (lane == 0) bulk_wait_all();
+    if (c == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------ plane backward
@@ -498,7 +513,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
 constexpr int kBwdK = 16;
 constexpr int kBwdConsumerWarps = 4;
 constexpr int kBwdThreads = (kBwdConsumerWarps + 1) * 32;
-constexpr int kBwdStages = 8;
+constexpr int kBwdStages = 20;  // 20 x 3.4 KB in flight per SM: enough bytes outstanding to cover HBM latency
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -571,17 +586,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     __syncthreads();
 
     if (warp == kBwdConsumerWarps) {
-        // ---- producer: one thread keeps the ring full ----
-        if (lane == 0) {
-            int it = 0;
-            for (int li = list_lo; li < list_hi; ++li, ++it) {
-                const int s = it % kBwdStages;
-                if (it >= kBwdStages) mbar_wait(empty + s, ((it / kBwdStages) - 1) & 1);
-                const int n = __ldg(order + li);
-                unsigned char* dst = ring + s * STAGE_BYTES;
-                mbar_expect_tx(full + s, STAGE_BYTES);
-                bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, full + s);
-                bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(LatticeRoi), full + s);
+        // ---- producer warp: keeps the ring full.  The list indices are fetched 32 at a time (one coalesced load)
+        // so that the issuing lane never waits on global memory between two bulk copies ----
+        int s = 0;
+        unsigned round = 0;  // how many times the ring has wrapped
+        for (int base = list_lo; base < list_hi; base += 32) {
+            const int mine = (base + lane < list_hi) ? __ldg(order + base + lane) : 0;
+            const int cnt = min(32, list_hi - base);
+            for (int j = 0; j < cnt; ++j) {
+                const int n = __shfl_sync(0xffffffffu, mine, j);
+                if (lane == 0) {
+                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                    unsigned char* dst = ring + s * STAGE_BYTES;
+                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, full + s);
+                    bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(LatticeRoi), full + s);
+                }
+                if (++s == kBwdStages) {
+                    s = 0;
+                    ++round;
+                }
             }
         }
         return;
@@ -591,10 +615,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     const int cl = lane >> 3, ph = lane & 7;
     const int c = warp * 4 + cl;
     float* plane = planes + (size_t)c * HWp;
-    int it = 0;
-    for (int li = list_lo; li < list_hi; ++li, ++it) {
-        const int s = it % kBwdStages;
-        mbar_wait(full + s, (it / kBwdStages) & 1);
+    int s = 0;
+    unsigned round = 0;
+    for (int li = list_lo; li < list_hi; ++li) {
+        mbar_wait(full + s, round & 1);
         const float* tile = reinterpret_cast<const float*>(ring + s * STAGE_BYTES);
         const LatticeRoi* t = reinterpret_cast<const LatticeRoi*>(ring + s * STAGE_BYTES + TILE_BYTES);
 
@@ -685,6 +709,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (++s == kBwdStages) {
+            s = 0;
+            ++round;
+        }
     }
     // ---- write this warp's four planes: the only write of these gradient bytes ----
     __syncwarp();
@@ -738,15 +766,15 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
     return I2V_OK;
 }
 
-static size_t plane_fwd_smem_bytes(int H, int W, int P) {
-    size_t stage = (size_t)kPlaneWarps * kPlaneK * P * P;
-    static_assert((size_t)kPlaneWarps * kPlaneK * 49 >= 2 * (size_t)kPlaneK * kFillPitch, "fill scratch fits the stage");
-    return ((size_t)H * W * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 2 * sizeof(PlaneTab);
+static size_t plane_fwd_smem_bytes(int H, int P) {
+    size_t stage = (size_t)kPlaneWarps * 2 * kPlaneK * P * P;
+    static_assert((size_t)kPlaneWarps * 2 * kPlaneK * 49 >= 2 * (size_t)kPlaneK * kFillPitch, "fill scratch fits the stage");
+    return ((size_t)H * kPitch * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 4 * sizeof(PlaneTab);
 }
 
 static bool plane_forward_ok(const float* out, int batch, int C, int H, int W, int PH, int PW) {
-    return batch > 0 && PH == 7 && PW == 7 && C % kPlaneK == 0 && H >= 2 && W >= 2 &&
-           plane_fwd_smem_bytes(H, W, 7) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0;
+    return batch > 0 && PH == 7 && PW == 7 && C % kPlaneK == 0 && H >= 2 && W >= 2 && W <= kPitch &&
+           plane_fwd_smem_bytes(H, 7) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0;
 }
 
 static int plane_split(int ctas) {
@@ -755,11 +783,11 @@ static int plane_split(int ctas) {
     return split;
 }
 
-template <int POOL, int WT>
-static int launch_plane_fwd_w(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
-                              cudaStream_t stream) {
-    auto kern = lattice_fwd_plane_kernel<7, POOL, WT>;
-    size_t smem = plane_fwd_smem_bytes(H, W, 7);
+template <int POOL>
+static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
+                            cudaStream_t stream) {
+    auto kern = lattice_fwd_plane_kernel<7, POOL>;
+    size_t smem = plane_fwd_smem_bytes(H, 7);
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctiles = C / kPlaneK;
     int split = plane_split(batch * ctiles);
@@ -767,6 +795,7 @@ static int launch_plane_fwd_w(const float* feat, const LatticeWs& w, float* out,
                                                                        H, W, split);
     return check_launch("lattice_fwd_plane_kernel");
 }
+
 static size_t plane_bwd_smem_bytes(int H, int W, int P) {
     return (size_t)kBwdStages * ((size_t)kBwdK * P * P * sizeof(float) + sizeof(LatticeRoi)) +
            2 * kBwdStages * sizeof(uint64_t) + (size_t)kBwdK * bwd_plane_pitch(H * W) * sizeof(float);
@@ -791,13 +820,6 @@ static int launch_plane_bwd(const float* grad_out, const LatticeWs& w, float* gr
                             cudaStream_t stream) {
     if (W == 63) return launch_plane_bwd_w<POOL, 63>(grad_out, w, grad_in, batch, C, H, W, stream);
     return launch_plane_bwd_w<POOL, 0>(grad_out, w, grad_in, batch, C, H, W, stream);
-}
-
-template <int POOL>
-static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
-                            cudaStream_t stream) {
-    if (W == 63) return launch_plane_fwd_w<POOL, 63>(feat, w, out, batch, C, H, W, stream);
-    return launch_plane_fwd_w<POOL, 0>(feat, w, out, batch, C, H, W, stream);
 }
 
 }  // namespace i2v
