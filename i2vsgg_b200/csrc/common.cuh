@@ -118,4 +118,16 @@ struct alignas(16) PlaneTab {
     float4 y[8];   // {byte offset of the upper row (int bits), weight of the upper row, weight of the lower row, 0}
 };
 
+// What the backward plane kernel needs of one RoI: offsets into a [H][W] fp32 plane and weights with the avg pool's
+// 1/4 folded in (zero for out-of-range lattice columns), plus the duplicate structure of the start cells.
+struct alignas(16) BwdTab {
+    int xoff[8];    // start column * 4 bytes
+    float wx0[8];   // weight of the left cell
+    float wx1[8];   // weight of the right cell
+    int yoff[8];    // start row * W * 4 bytes
+    float wy0[8];   // weight of the upper row
+    float wy1[8];   // weight of the lower row
+    unsigned valid_y, valid_x, y_runpos, y_maxrun, x_same, pad_[3];
+};
+
 }  // namespace i2v

@@ -53,7 +53,8 @@ __device__ __forceinline__ void lattice_axis(float lo, float hi, int G, int exte
 
 __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois, int batch, int H, int W, int GH,
                                     int GW, float scale, LatticeRoi* __restrict__ tab, int* __restrict__ roi_batch,
-                                    int* __restrict__ counts, PlaneTab* __restrict__ ptab, float ptab_scale) {
+                                    int* __restrict__ counts, PlaneTab* __restrict__ ptab, float ptab_scale,
+                                    BwdTab* __restrict__ btab) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= num_rois) return;
     const float* r = rois + (size_t)n * 5;
@@ -102,6 +103,26 @@ __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois
                                  oky ? t.y.frac[p] : 0.f, 0.f);
         }
         ptab[n] = q;
+    }
+    if (btab) {  // the backward plane kernel's view
+        BwdTab q;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            bool okx = (t.valid_x >> p) & 1u;
+            q.xoff[p] = t.x.start[p] * 4;
+            q.wx0[p] = okx ? (1.f - t.x.frac[p]) * ptab_scale : 0.f;
+            q.wx1[p] = okx ? t.x.frac[p] * ptab_scale : 0.f;
+            q.yoff[p] = t.y.start[p] * W * 4;
+            q.wy0[p] = 1.f - t.y.frac[p];
+            q.wy1[p] = t.y.frac[p];
+        }
+        q.valid_y = t.valid_y;
+        q.valid_x = t.valid_x;
+        q.y_runpos = t.y_runpos;
+        q.y_maxrun = t.y_maxrun;
+        q.x_same = t.x_same;
+        q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
+        btab[n] = q;
     }
     // RoIs whose batch index is out of range are listed in the extra bucket `batch` (their rows are zero-filled)
     if (roi_batch) roi_batch[n] = in_batch ? b : batch;
@@ -260,8 +281,6 @@ __global__ void __launch_bounds__(256) lattice_bwd_gather_kernel(const float* __
 constexpr int kPlaneK = 16;        // channels per CTA
 constexpr int kPlaneWarps = 9;     // warps per CTA (each works on two RoIs at a time)
 constexpr int kPlaneThreads = kPlaneWarps * 32;
-constexpr int kFillCells = 384;    // cells per fill round
-constexpr int kFillPitch = 386;    // == 2 (mod 32): the transposing read of a round is bank-conflict free
 
 __device__ __forceinline__ void bulk_store_commit(float* gdst, const float* ssrc, unsigned bytes) {
     unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
@@ -336,55 +355,26 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
         return;
     }
 
-    // ---- fill: 16 planes, global [c][row][col] -> shared [row][col][16].  Rounds of whole rows stream through a
-    // double buffered [16][386] scratch with cp.async: the copy of round r+1 overlaps the transposition of round r.
-    // Index math is per warp-wide item (64 cells of one plane / one pair of cells x 16 channels), not per element ----
+    // ---- fill: 16 planes, global [c][row][col] -> shared [row][col][16], straight into the final layout with 4-byte
+    // cp.async: a warp-wide copy moves two adjacent cells x 16 channels = 128 contiguous shared bytes (conflict free);
+    // on the global side it touches 8 bytes of 16 sectors, whose remaining bytes are picked up from L1 by the next
+    // three copies.  Every copy of the CTA is in flight before the single wait: latency is paid once ----
     {
         const int HW = H * W;
-        const float* src = feat + ((size_t)b * C + (size_t)ct * kPlaneK) * HW;
-        const int rpr = kFillCells / W;  // rows per round
-        const int round_cells = rpr * W;
-        const int rounds = ceil_div(H, rpr);
-        const int nseg = ceil_div(round_cells, 64);
-        const bool pairs = ((HW | round_cells) & 1) == 0 && (((uintptr_t)feat & 7) == 0);  // 8-byte copies allowed
-        auto issue = [&](int r) {
-            float* scr = stage + (r & 1) * (kPlaneK * kFillPitch);
-            const int c0 = r * round_cells;
-            const int ncell = min(round_cells, HW - c0);
-            for (int item = warp; item < kPlaneK * nseg; item += kPlaneWarps) {
-                const int cc = item / nseg, seg = item - cc * nseg;
-                const int x = seg * 64 + lane * 2;
-                const float* g = src + (size_t)cc * HW + c0 + x;
-                float* d = scr + cc * kFillPitch + x;
-                if (pairs) {
-                    if (x < ncell) cp_async8(d, g);
-                } else {
-                    if (x < ncell) cp_async4(d, g);
-                    if (x + 1 < ncell) cp_async4(d + 1, g + 1);
-                }
-            }
-            cp_async_commit();
-        };
-        issue(0);
         const int tc = lane & 15, tdx = lane >> 4;
-        for (int r = 0; r < rounds; ++r) {
-            if (r + 1 < rounds) {
-                issue(r + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+        const float* src = feat + ((size_t)b * C + (size_t)ct * kPlaneK + tc) * HW + tdx;
+        float* dst = planes + tdx * kPlaneK + tc;
+        for (int row = warp; row < H; row += kPlaneWarps) {
+            const float* g = src + row * W;
+            float* d = dst + (size_t)row * kPitch * kPlaneK;
+#pragma unroll 4
+            for (int j = 0; j < kPitch / 2; ++j) {
+                if (2 * j + tdx < W) cp_async4(d + j * 2 * kPlaneK, g + 2 * j);
             }
-            __syncthreads();
-            const float* scr = stage + (r & 1) * (kPlaneK * kFillPitch) + tc * kFillPitch;
-            const int row0 = r * rpr;
-            const int nrow = min(rpr, H - row0);
-            // one item = two adjacent cells of one row x 16 channels: conflict-free read, 128 contiguous bytes written
-            for (int item = warp; item < nrow * 32; item += kPlaneWarps) {
-                const int ry = item >> 5, rx = (item & 31) * 2 + tdx;
-                if (rx < W) planes[((size_t)(row0 + ry) * kPitch + rx) * kPlaneK + tc] = scr[ry * W + rx];
-            }
-            __syncthreads();
         }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
     }
 
     // shared-window byte address of this lane's channel in cell (0,0)
@@ -432,14 +422,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
         unsigned xfirst[G], xsecond[G];
         float wfirst[G], wsecond[G];
         {
-            const float4* xe = role ? t->xb : t->xa;
+            // asm volatile: the compiler must keep these 32 values in registers instead of re-reading the table per row
+            const unsigned xe = (unsigned)__cvta_generic_to_shared(role ? t->xb : t->xa);
 #pragma unroll
             for (int p = 0; p < G; ++p) {
-                float4 e = xe[p];
-                xfirst[p] = (unsigned)__float_as_int(e.x);
-                wfirst[p] = e.y;
-                xsecond[p] = (unsigned)__float_as_int(e.z);
-                wsecond[p] = e.w;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(xfirst[p]), "=f"(wfirst[p]), "=r"(xsecond[p]), "=f"(wsecond[p])
+                             : "r"(xe + p * 16));
             }
         }
         float part[NOUT];
@@ -551,14 +540,14 @@ __host__ __device__ inline int bwd_plane_pitch(int HW) { return HW + ((8 - HW % 
 
 template <int P, int POOL, int WT>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-    lattice_bwd_plane_kernel(const float* __restrict__ grad_out, const LatticeRoi* __restrict__ tab,
+    lattice_bwd_plane_kernel(const float* __restrict__ grad_out, const BwdTab* __restrict__ tab,
                              const int* __restrict__ order, const int* __restrict__ starts,
                              float* __restrict__ grad_in, int C, int H, int Wrt) {
     constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
     constexpr int NOUT = P * P;
     constexpr int TILE_BYTES = kBwdK * NOUT * (int)sizeof(float);
-    constexpr int STAGE_BYTES = TILE_BYTES + (int)sizeof(LatticeRoi);
-    static_assert(G <= 8 && TILE_BYTES % 16 == 0 && sizeof(LatticeRoi) % 16 == 0, "stage layout");
+    constexpr int STAGE_BYTES = TILE_BYTES + (int)sizeof(BwdTab);
+    static_assert(G <= 8 && TILE_BYTES % 16 == 0 && sizeof(BwdTab) % 16 == 0, "stage layout");
     extern __shared__ __align__(128) unsigned char bsmem[];
     const int W = WT ? WT : Wrt;
     const int HW = H * W;
@@ -600,7 +589,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
                     unsigned char* dst = ring + s * STAGE_BYTES;
                     mbar_expect_tx(full + s, STAGE_BYTES);
                     bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, full + s);
-                    bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(LatticeRoi), full + s);
+                    bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(BwdTab), full + s);
                 }
                 if (++s == kBwdStages) {
                     s = 0;
@@ -620,90 +609,104 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     for (int li = list_lo; li < list_hi; ++li) {
         mbar_wait(full + s, round & 1);
         const float* tile = reinterpret_cast<const float*>(ring + s * STAGE_BYTES);
-        const LatticeRoi* t = reinterpret_cast<const LatticeRoi*>(ring + s * STAGE_BYTES + TILE_BYTES);
+        const BwdTab* t = reinterpret_cast<const BwdTab*>(ring + s * STAGE_BYTES + TILE_BYTES);
 
         const unsigned vx = t->valid_x, vy = t->valid_y, xsame = t->x_same;
         const int maxrun = (int)t->y_maxrun;
-        const unsigned ax = vx & ~xsame & ((1u << G) - 1u);  // columns that still own a pair of cells after merging
+        constexpr unsigned FULL = (1u << G) - 1u;
+        const unsigned ax = vx & ~xsame & FULL;  // columns that still own a pair of cells after merging
         if (maxrun > 0 && ax != 0u) {
-            // uniform column tables
-            int xs[G];
-            float wx0[G], wx1[G];
-            {
-                const int4* qs = reinterpret_cast<const int4*>(t->x.start);
-                const float4* qf = reinterpret_cast<const float4*>(t->x.frac);
-                int4 s0 = qs[0], s1 = qs[1];
-                float4 f0 = qf[0], f1 = qf[1];
-                const int si[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float fi[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-                const float q = (POOL == I2V_POOL_AVG) ? 0.25f : 1.f;
-#pragma unroll
-                for (int p = 0; p < G; ++p) {
-                    bool ok = (vx >> p) & 1u;
-                    xs[p] = si[p];
-                    wx0[p] = ok ? (1.f - fi[p]) * q : 0.f;
-                    wx1[p] = ok ? fi[p] * q : 0.f;
-                }
-            }
-            // this lane's lattice row
-            const bool oky = (ph < G) && ((vy >> ph) & 1u);
-            const int ys = t->y.start[ph & (kMaxLattice - 1)];
-            const float yf = t->y.frac[ph & (kMaxLattice - 1)];
-            const int myrun = (int)((t->y_runpos >> (4 * ph)) & 15u);
+            // this lane's lattice row of gradients; the pool's backward collects (ph-1..ph) x (pw-1..pw)
             float gl[G];
             if (POOL == I2V_POOL_NONE) {
 #pragma unroll
                 for (int pw = 0; pw < G; ++pw) gl[pw] = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + pw] : 0.f;
             } else {
-                // pool backward: lattice point (ph,pw) collects the pooled cells (ph-1..ph, pw-1..pw)
-                float own[P], up[P];
+                float sv[P];
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    own[j] = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + j] : 0.f;
-                    up[j] = (ph >= 1) ? tile[c * NOUT + max(ph - 1, 0) * P + j] : 0.f;
+                    float own = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + j] : 0.f;
+                    float up = (ph >= 1) ? tile[c * NOUT + max(ph - 1, 0) * P + j] : 0.f;
+                    sv[j] = own + up;
                 }
+                gl[0] = sv[0];
 #pragma unroll
-                for (int pw = 0; pw < G; ++pw) {
-                    float v = 0.f;
-                    if (pw >= 1) v += own[pw - 1] + up[pw - 1];
-                    if (pw < P) v += own[pw] + up[pw];
-                    gl[pw] = v;
-                }
+                for (int pw = 1; pw < P; ++pw) gl[pw] = sv[pw - 1] + sv[pw];
+                gl[P] = sv[P - 1];
             }
+            // uniform column tables (byte offsets, weights with validity and the pool's 1/4 folded in)
+            int xo[G];
             float t0[G], t1[G];
+            {
+                const int4* qo = reinterpret_cast<const int4*>(t->xoff);
+                const float4* q0 = reinterpret_cast<const float4*>(t->wx0);
+                const float4* q1 = reinterpret_cast<const float4*>(t->wx1);
+                int4 oa = qo[0], ob = qo[1];
+                float4 a0 = q0[0], b0 = q0[1], a1 = q1[0], b1 = q1[1];
+                const int xi[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+                const float w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+                const float w1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int pw = 0; pw < G; ++pw) {
-                t0[pw] = gl[pw] * wx0[pw];
-                t1[pw] = gl[pw] * wx1[pw];
-            }
-            if (xsame != 0u) {  // merge columns that share their start cell into the first of the run
-#pragma unroll
-                for (int pw = G - 2; pw >= 0; --pw) {
-                    if ((xsame >> (pw + 1)) & 1u) {
-                        t0[pw] += t0[pw + 1];
-                        t1[pw] += t1[pw + 1];
-                    }
+                for (int p = 0; p < G; ++p) {
+                    xo[p] = xi[p];
+                    t0[p] = gl[p] * w0[p];
+                    t1[p] = gl[p] * w1[p];
                 }
             }
-            const float wy0 = 1.f - yf, wy1 = yf;
-            float* row0 = plane + ys * W;
-            for (int k = 0; k < maxrun; ++k) {
-                const bool act = oky && (myrun == k);
+            const bool oky = (ph < G) && ((vy >> ph) & 1u);
+            const float wy0 = t->wy0[ph], wy1 = t->wy1[ph];
+            char* row0 = reinterpret_cast<char*>(plane) + t->yoff[ph];
+            const int row_bytes = W * 4;
+            if (maxrun == 1 && ax == FULL) {
+                // ---- common case: every column owns its cells, no two lattice rows share a start row ----
 #pragma unroll
                 for (int dy = 0; dy < 2; ++dy) {
-                    float* row = row0 + (dy ? W : 0);
+                    char* row = row0 + (dy ? row_bytes : 0);
                     const float wy = dy ? wy1 : wy0;
 #pragma unroll
                     for (int dxx = 0; dxx < 2; ++dxx) {
                         float old[G];
 #pragma unroll
-                        for (int pw = 0; pw < G; ++pw)
-                            if (act && ((ax >> pw) & 1u)) old[pw] = row[xs[pw] + dxx];
+                        for (int pw = 0; pw < G; ++pw) old[pw] = *reinterpret_cast<float*>(row + xo[pw] + dxx * 4);
 #pragma unroll
-                        for (int pw = 0; pw < G; ++pw)
-                            if (act && ((ax >> pw) & 1u)) row[xs[pw] + dxx] = old[pw] + (dxx ? t1[pw] : t0[pw]) * wy;
+                        for (int pw = 0; pw < G; ++pw) old[pw] += (dxx ? t1[pw] : t0[pw]) * wy;
+                        if (oky) {
+#pragma unroll
+                            for (int pw = 0; pw < G; ++pw) *reinterpret_cast<float*>(row + xo[pw] + dxx * 4) = old[pw];
+                        }
                     }
                     __syncwarp();
+                }
+            } else {
+                if (xsame != 0u) {  // merge columns that share their start cell into the first of the run
+#pragma unroll
+                    for (int pw = G - 2; pw >= 0; --pw) {
+                        if ((xsame >> (pw + 1)) & 1u) {
+                            t0[pw] += t0[pw + 1];
+                            t1[pw] += t1[pw + 1];
+                        }
+                    }
+                }
+                const int myrun = (int)((t->y_runpos >> (4 * ph)) & 15u);
+                for (int k = 0; k < maxrun; ++k) {
+                    const bool act = oky && (myrun == k);
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) {
+                        char* row = row0 + (dy ? row_bytes : 0);
+                        const float wy = dy ? wy1 : wy0;
+#pragma unroll
+                        for (int dxx = 0; dxx < 2; ++dxx) {
+                            float old[G];
+#pragma unroll
+                            for (int pw = 0; pw < G; ++pw)
+                                if (act && ((ax >> pw) & 1u)) old[pw] = *reinterpret_cast<float*>(row + xo[pw] + dxx * 4);
+#pragma unroll
+                            for (int pw = 0; pw < G; ++pw)
+                                if (act && ((ax >> pw) & 1u))
+                                    *reinterpret_cast<float*>(row + xo[pw] + dxx * 4) = old[pw] + (dxx ? t1[pw] : t0[pw]) * wy;
+                        }
+                        __syncwarp();
+                    }
                 }
             }
         }
@@ -726,7 +729,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 // ------------------------------------------------------------------------------------------ host side
 struct LatticeWs {
     LatticeRoi* tab;
-    PlaneTab* ptab;
+    PlaneTab* ptab;   // the plane tables share one allocation: the forward view or the backward view of a call
+    BwdTab* btab;
     int* roi_batch;
     int* counts;
     int* starts;
@@ -745,19 +749,23 @@ static LatticeWs carve_lattice_ws(void* ws, int batch, int num_rois, bool lists 
         w.starts = cv.take<int>((size_t)batch + 2);
         w.order = cv.take<int>((size_t)num_rois);
         w.ptab = cv.take<PlaneTab>((size_t)num_rois);
+        w.btab = reinterpret_cast<BwdTab*>(w.ptab);
+        static_assert(sizeof(BwdTab) <= sizeof(PlaneTab), "the backward table reuses the forward table's slot");
     }
     w.bytes = cv.used();
     return w;
 }
 
 static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W, int GH, int GW, float scale,
-                        const LatticeWs& w, bool lists, cudaStream_t stream, float ptab_scale = 0.f) {
+                        const LatticeWs& w, bool lists, cudaStream_t stream, float ptab_scale = 0.f,
+                        bool backward = false) {
     if (lists) I2V_CUDA_TRY(cudaMemsetAsync(w.counts, 0, sizeof(int) * ((size_t)batch + 2), stream));
     lattice_prep_kernel<<<ceil_div(num_rois, 128), 128, 0, stream>>>(rois, num_rois, batch, H, W, GH, GW, scale, w.tab,
                                                                      lists ? w.roi_batch : nullptr,
                                                                      lists ? w.counts : nullptr,
-                                                                     (lists && ptab_scale != 0.f) ? w.ptab : nullptr,
-                                                                     ptab_scale);
+                                                                     (lists && ptab_scale != 0.f && !backward) ? w.ptab : nullptr,
+                                                                     ptab_scale,
+                                                                     (lists && ptab_scale != 0.f && backward) ? w.btab : nullptr);
     I2V_TRY(check_launch("lattice_prep_kernel"));
     if (lists) {
         roi_bucket_kernel<<<batch + 1, 256, 0, stream>>>(w.roi_batch, num_rois, batch + 1, w.counts, w.starts, w.order);
@@ -768,7 +776,6 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
 
 static size_t plane_fwd_smem_bytes(int H, int P) {
     size_t stage = (size_t)kPlaneWarps * 2 * kPlaneK * P * P;
-    static_assert((size_t)kPlaneWarps * 2 * kPlaneK * 49 >= 2 * (size_t)kPlaneK * kFillPitch, "fill scratch fits the stage");
     return ((size_t)H * kPitch * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 4 * sizeof(PlaneTab);
 }
 
@@ -797,7 +804,7 @@ static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, i
 }
 
 static size_t plane_bwd_smem_bytes(int H, int W, int P) {
-    return (size_t)kBwdStages * ((size_t)kBwdK * P * P * sizeof(float) + sizeof(LatticeRoi)) +
+    return (size_t)kBwdStages * ((size_t)kBwdK * P * P * sizeof(float) + sizeof(BwdTab)) +
            2 * kBwdStages * sizeof(uint64_t) + (size_t)kBwdK * bwd_plane_pitch(H * W) * sizeof(float);
 }
 
@@ -812,7 +819,7 @@ static int launch_plane_bwd_w(const float* grad_out, const LatticeWs& w, float* 
     auto kern = lattice_bwd_plane_kernel<7, POOL, WT>;
     size_t smem = plane_bwd_smem_bytes(H, W, 7);
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<batch * (C / kBwdK), kBwdThreads, smem, stream>>>(grad_out, w.tab, w.order, w.starts, grad_in, C, H, W);
+    kern<<<batch * (C / kBwdK), kBwdThreads, smem, stream>>>(grad_out, w.btab, w.order, w.starts, grad_in, C, H, W);
     return check_launch("lattice_bwd_plane_kernel");
 }
 template <int POOL>
@@ -915,7 +922,8 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
     }
     if (can_plane && impl != I2V_IMPL_GATHER) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
-        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream,
+                             pool_mode == I2V_POOL_AVG ? 0.25f : 1.f, true));
         if (pool_mode == I2V_POOL_AVG) return launch_plane_bwd<I2V_POOL_AVG>(grad_out, w, grad_in, batch, channels, height, width, stream);
         return launch_plane_bwd<I2V_POOL_NONE>(grad_out, w, grad_in, batch, channels, height, width, stream);
     }
