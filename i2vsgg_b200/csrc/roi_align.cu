@@ -489,9 +489,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
 // ------------------------------------------------------------------------------------------ plane backward
 // One CTA per (frame, 16 channels) OWNS those 16 gradient planes: they are accumulated in shared memory and written
 // to HBM exactly once, so there is no global atomic, no pre-zeroing pass and the result is deterministic.
-// Inside the CTA every consumer warp owns 4 of the planes; its 32 lanes are (channel 0-3) x (lattice row 0-7) and
-// walk the frame's RoIs in list order.  For one RoI a lane forms its row of lattice gradients (the pool's backward
-// is two adds), weights it per column, and adds it to the two feature rows it touches with plain
+// Inside the CTA every consumer warp owns one CHANNEL PAIR, stored interleaved as float2 cells so that one
+// ld.shared.v2 / fma.rn.f32x2 / st.shared.v2 updates both channels of a cell; its 32 lanes are (lattice row 0-7) x
+// (column pair 0-3) and walk the frame's RoIs in list order.  For one RoI a lane forms its two lattice gradients (the
+// pool's backward is a few adds), weights them per column, and adds them to the cells they touch with plain
 // load / fma / store -- no atomics are needed because
 //   * rows of different lattice rows are distinct cells unless the start cells repeat, and repeated start cells
 //     are serialised by their position in the run (y_runpos), one __syncwarp apart;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
 // The pooled-gradient tiles ([16][P*P] floats, contiguous in NCHW) and the RoI tables stream in through a TMA bulk
 // copy ring fed by a producer warp, so HBM latency is hidden without occupancy.
 constexpr int kBwdK = 16;
-constexpr int kBwdConsumerWarps = 4;
+constexpr int kBwdConsumerWarps = 8;
 constexpr int kBwdThreads = (kBwdConsumerWarps + 1) * 32;
 constexpr int kBwdStages = 20;  // 20 x 3.4 KB in flight per SM: enough bytes outstanding to cover HBM latency
 
@@ -534,6 +535,20 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned
                      (unsigned)__cvta_generic_to_shared(sdst)),
                  "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
                  : "memory");
+}
+
+// Packed fp32x2 fused multiply-add (FFMA2): both channels of a cell in one instruction.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %5};\n"
+        "mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
 }
 
 __host__ __device__ inline int bwd_plane_pitch(int HW) { return HW + ((8 - HW % 32) + 32) % 32; }  // == 8 (mod 32)
@@ -575,35 +590,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     __syncthreads();
 
     if (warp == kBwdConsumerWarps) {
-        // ---- producer warp: keeps the ring full.  The list indices are fetched 32 at a time (one coalesced load)
-        // so that the issuing lane never waits on global memory between two bulk copies ----
-        int s = 0;
-        unsigned round = 0;  // how many times the ring has wrapped
-        for (int base = list_lo; base < list_hi; base += 32) {
-            const int mine = (base + lane < list_hi) ? __ldg(order + base + lane) : 0;
-            const int cnt = min(32, list_hi - base);
-            for (int j = 0; j < cnt; ++j) {
-                const int n = __shfl_sync(0xffffffffu, mine, j);
-                if (lane == 0) {
-                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                    unsigned char* dst = ring + s * STAGE_BYTES;
-                    mbar_expect_tx(full + s, STAGE_BYTES);
-                    bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, full + s);
-                    bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(BwdTab), full + s);
-                }
-                if (++s == kBwdStages) {
-                    s = 0;
-                    ++round;
-                }
+        // ---- producer warp: lane j feeds ring stage j, so up to kBwdStages bulk copies are issued side by side and
+        // the (slow, single-thread) barrier handshake of one stage never holds up another ----
+        if (lane < kBwdStages) {
+            uint64_t* my_full = full + lane;
+            uint64_t* my_empty = empty + lane;
+            unsigned char* dst = ring + lane * STAGE_BYTES;
+            unsigned round = 0;
+            for (int li = list_lo + lane; li < list_hi; li += kBwdStages, ++round) {
+                const int n = __ldg(order + li);
+                if (round > 0) mbar_wait(my_empty, (round - 1) & 1);
+                mbar_expect_tx(my_full, STAGE_BYTES);
+                bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kBwdK) * NOUT, TILE_BYTES, my_full);
+                bulk_load(dst + TILE_BYTES, tab + n, (unsigned)sizeof(BwdTab), my_full);
             }
         }
         return;
     }
 
-    // ---- consumers ----
-    const int cl = lane >> 3, ph = lane & 7;
-    const int c = warp * 4 + cl;
-    float* plane = planes + (size_t)c * HWp;
+    // ---- consumers: warp w owns the channel pair (2w, 2w+1); lanes = (lattice row 0-7) x (column pair 0-3) ----
+    const int ph = lane >> 2, xq = lane & 3;
+    const int c0 = warp * 2;
+    float2* plane = reinterpret_cast<float2*>(planes) + (size_t)warp * HWp;   // [HWp] cells of (c0, c0+1)
+    // which pooled rows / columns this lane's two lattice points (ph, 2xq) and (ph, 2xq+1) collect (pool backward)
+    const float m_own = (ph < P) ? 1.f : 0.f, m_up = (ph >= 1) ? 1.f : 0.f;
+    const int jl = max(2 * xq - 1, 0), jm = min(2 * xq, P - 1), jr = min(2 * xq + 1, P - 1);
+    const float m_l = (2 * xq - 1 >= 0) ? 1.f : 0.f, m_m = (2 * xq < P) ? 1.f : 0.f, m_r = (2 * xq + 1 < P) ? 1.f : 0.f;
+    const int row_own = min(ph, P - 1) * P, row_up = max(ph - 1, 0) * P;
     int s = 0;
     unsigned round = 0;
     for (int li = list_lo; li < list_hi; ++li) {
@@ -616,96 +629,91 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         constexpr unsigned FULL = (1u << G) - 1u;
         const unsigned ax = vx & ~xsame & FULL;  // columns that still own a pair of cells after merging
         if (maxrun > 0 && ax != 0u) {
-            // this lane's lattice row of gradients; the pool's backward collects (ph-1..ph) x (pw-1..pw)
-            float gl[G];
-            if (POOL == I2V_POOL_NONE) {
-#pragma unroll
-                for (int pw = 0; pw < G; ++pw) gl[pw] = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + pw] : 0.f;
-            } else {
-                float sv[P];
-#pragma unroll
-                for (int j = 0; j < P; ++j) {
-                    float own = (ph < P) ? tile[c * NOUT + min(ph, P - 1) * P + j] : 0.f;
-                    float up = (ph >= 1) ? tile[c * NOUT + max(ph - 1, 0) * P + j] : 0.f;
-                    sv[j] = own + up;
-                }
-                gl[0] = sv[0];
-#pragma unroll
-                for (int pw = 1; pw < P; ++pw) gl[pw] = sv[pw - 1] + sv[pw];
-                gl[P] = sv[P - 1];
-            }
-            // uniform column tables (byte offsets, weights with validity and the pool's 1/4 folded in)
-            int xo[G];
-            float t0[G], t1[G];
+            // lattice gradients of this lane's two points, for both channels (x = channel c0, y = channel c0+1)
+            float2 gl0, gl1;
             {
-                const int4* qo = reinterpret_cast<const int4*>(t->xoff);
-                const float4* q0 = reinterpret_cast<const float4*>(t->wx0);
-                const float4* q1 = reinterpret_cast<const float4*>(t->wx1);
-                int4 oa = qo[0], ob = qo[1];
-                float4 a0 = q0[0], b0 = q0[1], a1 = q1[0], b1 = q1[1];
-                const int xi[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-                const float w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-                const float w1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int p = 0; p < G; ++p) {
-                    xo[p] = xi[p];
-                    t0[p] = gl[p] * w0[p];
-                    t1[p] = gl[p] * w1[p];
+                const float* ta = tile + c0 * NOUT;
+                const float* tb = ta + NOUT;
+                if (POOL == I2V_POOL_NONE) {
+                    gl0 = make_float2(ta[row_own + jm] * (m_own * m_m), tb[row_own + jm] * (m_own * m_m));
+                    gl1 = make_float2(ta[row_own + jr] * (m_own * m_r), tb[row_own + jr] * (m_own * m_r));
+                } else {
+                    // sum over the pooled rows (ph-1, ph) first, then over the pooled columns (pw-1, pw)
+                    float al = ta[row_own + jl] * m_own + ta[row_up + jl] * m_up, bl = tb[row_own + jl] * m_own + tb[row_up + jl] * m_up;
+                    float am = ta[row_own + jm] * m_own + ta[row_up + jm] * m_up, bm = tb[row_own + jm] * m_own + tb[row_up + jm] * m_up;
+                    float ar = ta[row_own + jr] * m_own + ta[row_up + jr] * m_up, br = tb[row_own + jr] * m_own + tb[row_up + jr] * m_up;
+                    gl0 = make_float2(al * m_l + am * m_m, bl * m_l + bm * m_m);
+                    gl1 = make_float2(am * m_m + ar * m_r, bm * m_m + br * m_r);
                 }
             }
+            // column tables of this lane's two columns: byte offsets (float2 cells) and weights (validity, 1/4 folded in)
+            const int2 xo = reinterpret_cast<const int2*>(t->xoff)[xq];
+            const float2 w0 = reinterpret_cast<const float2*>(t->wx0)[xq];
+            const float2 w1 = reinterpret_cast<const float2*>(t->wx1)[xq];
+            float2 t00 = make_float2(gl0.x * w0.x, gl0.y * w0.x), t01 = make_float2(gl0.x * w1.x, gl0.y * w1.x);  // column 2xq: left, right cell
+            float2 t10 = make_float2(gl1.x * w0.y, gl1.y * w0.y), t11 = make_float2(gl1.x * w1.y, gl1.y * w1.y);  // column 2xq+1
             const bool oky = (ph < G) && ((vy >> ph) & 1u);
             const float wy0 = t->wy0[ph], wy1 = t->wy1[ph];
-            char* row0 = reinterpret_cast<char*>(plane) + t->yoff[ph];
-            const int row_bytes = W * 4;
+            char* row0 = reinterpret_cast<char*>(plane) + 2 * t->yoff[ph];   // tables hold 4-byte cell offsets
+            char* pa = row0 + 2 * xo.x;
+            char* pb = row0 + 2 * xo.y;
+            const int row_bytes = W * 8;
             if (maxrun == 1 && ax == FULL) {
-                // ---- common case: every column owns its cells, no two lattice rows share a start row ----
+                // ---- common case: every column owns its cells, no two lattice rows share a start row.  Four phases
+                // (upper/lower row x left/right cell); inside a phase all 64 cells of the warp are distinct ----
 #pragma unroll
                 for (int dy = 0; dy < 2; ++dy) {
-                    char* row = row0 + (dy ? row_bytes : 0);
-                    const float wy = dy ? wy1 : wy0;
+                    const float2 wy = dy ? make_float2(wy1, wy1) : make_float2(wy0, wy0);
 #pragma unroll
                     for (int dxx = 0; dxx < 2; ++dxx) {
-                        float old[G];
-#pragma unroll
-                        for (int pw = 0; pw < G; ++pw) old[pw] = *reinterpret_cast<float*>(row + xo[pw] + dxx * 4);
-#pragma unroll
-                        for (int pw = 0; pw < G; ++pw) old[pw] += (dxx ? t1[pw] : t0[pw]) * wy;
+                        float2* qa = reinterpret_cast<float2*>(pa + (dy ? row_bytes : 0) + dxx * 8);
+                        float2* qb = reinterpret_cast<float2*>(pb + (dy ? row_bytes : 0) + dxx * 8);
+                        float2 oa = *qa, ob = *qb;
+                        oa = ffma2(dxx ? t01 : t00, wy, oa);
+                        ob = ffma2(dxx ? t11 : t10, wy, ob);
                         if (oky) {
-#pragma unroll
-                            for (int pw = 0; pw < G; ++pw) *reinterpret_cast<float*>(row + xo[pw] + dxx * 4) = old[pw];
+                            *qa = oa;
+                            if (G % 2 == 0 || 2 * xq + 1 < G) *qb = ob;   // odd lattices have no column G
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             } else {
-                if (xsame != 0u) {  // merge columns that share their start cell into the first of the run
+                // ---- general case: merge columns that share a start cell into the first column of their run (the
+                // run may cross lanes), serialise lattice rows that share a start row by their position in the run ----
+                if (xsame != 0u) {
 #pragma unroll
-                    for (int pw = G - 2; pw >= 0; --pw) {
-                        if ((xsame >> (pw + 1)) & 1u) {
-                            t0[pw] += t0[pw + 1];
-                            t1[pw] += t1[pw + 1];
+                    for (int pw = G - 1; pw >= 1; --pw) {
+                        if ((xsame >> pw) & 1u) {   // uniform: column pw folds into column pw-1
+                            if (pw & 1) {            // both columns live in the same lane
+                                if (xq == (pw >> 1)) {
+                                    t00.x += t10.x; t00.y += t10.y; t01.x += t11.x; t01.y += t11.y;
+                                }
+                            } else {                 // column pw is the first of lane pw/2, column pw-1 the second of lane pw/2 - 1
+                                float sx0 = __shfl_down_sync(0xffffffffu, t00.x, 1), sy0 = __shfl_down_sync(0xffffffffu, t00.y, 1);
+                                float sx1 = __shfl_down_sync(0xffffffffu, t01.x, 1), sy1 = __shfl_down_sync(0xffffffffu, t01.y, 1);
+                                if (xq == (pw >> 1) - 1) {
+                                    t10.x += sx0; t10.y += sy0; t11.x += sx1; t11.y += sy1;
+                                }
+                            }
                         }
                     }
                 }
+                const bool own_a = (ax >> (2 * xq)) & 1u, own_b = (ax >> (2 * xq + 1)) & 1u;
                 const int myrun = (int)((t->y_runpos >> (4 * ph)) & 15u);
                 for (int k = 0; k < maxrun; ++k) {
                     const bool act = oky && (myrun == k);
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy) {
-                        char* row = row0 + (dy ? row_bytes : 0);
-                        const float wy = dy ? wy1 : wy0;
+                        const float2 wy = dy ? make_float2(wy1, wy1) : make_float2(wy0, wy0);
 #pragma unroll
                         for (int dxx = 0; dxx < 2; ++dxx) {
-                            float old[G];
-#pragma unroll
-                            for (int pw = 0; pw < G; ++pw)
-                                if (act && ((ax >> pw) & 1u)) old[pw] = *reinterpret_cast<float*>(row + xo[pw] + dxx * 4);
-#pragma unroll
-                            for (int pw = 0; pw < G; ++pw)
-                                if (act && ((ax >> pw) & 1u))
-                                    *reinterpret_cast<float*>(row + xo[pw] + dxx * 4) = old[pw] + (dxx ? t1[pw] : t0[pw]) * wy;
+                            float2* qa = reinterpret_cast<float2*>(pa + (dy ? row_bytes : 0) + dxx * 8);
+                            float2* qb = reinterpret_cast<float2*>(pb + (dy ? row_bytes : 0) + dxx * 8);
+                            if (act && own_a) *qa = ffma2(dxx ? t01 : t00, wy, *qa);
+                            if (act && own_b) *qb = ffma2(dxx ? t11 : t10, wy, *qb);
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
             }
@@ -717,12 +725,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
             ++round;
         }
     }
-    // ---- write this warp's four planes: the only write of these gradient bytes ----
+    // ---- write this warp's two planes: the only write of these gradient bytes ----
     __syncwarp();
-    float* dst = grad_in + ((size_t)b * C + (size_t)ct * kBwdK + (size_t)warp * 4) * HW;
-    for (int q = 0; q < 4; ++q) {
-        const float* src = planes + (size_t)(warp * 4 + q) * HWp;
-        for (int i = lane; i < HW; i += 32) dst[(size_t)q * HW + i] = src[i];
+    float* dst = grad_in + ((size_t)b * C + (size_t)ct * kBwdK + (size_t)c0) * HW;
+    for (int i = lane; i < HW; i += 32) {
+        float2 v = plane[i];
+        dst[i] = v.x;
+        dst[(size_t)HW + i] = v.y;
     }
 }
 
