@@ -14,8 +14,9 @@ OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 IMPL_AUTO, IMPL_GATHER, IMPL_PLANE = 0, 1, 2
 ARGMAX_FLAT, ARGMAX_PLANE = 0, 1
+DT_F32, DT_BF16, DT_TF32 = 0, 1, 2
 
-_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_vp, _i, _f, _sz, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 
 # name -> (restype, argtypes); mirrors include/i2vsgg_b200.h one to one
 SIGNATURES = {
@@ -43,6 +44,11 @@ SIGNATURES = {
     "i2v_pair_build": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "i2v_triplet_topk_workspace_bytes": (_sz, [_i, _i]),
     "i2v_triplet_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_roi_pool_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _ll, _i, _vp]),
+    "i2v_linear_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _vp]),
+    "i2v_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp]),
+    "i2v_rel_scores_workspace_bytes": (_sz, [_i, _i]),
+    "i2v_rel_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

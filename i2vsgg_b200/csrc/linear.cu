@@ -1,0 +1,419 @@
+// The dense projection of the SGG stage on the 5th-generation tensor cores of sm_100a:
+//     y[M,N] = act(x[M,K] . W[N,K]^T + bias[N])
+// which is every FC layer of vrd.forward (lib/model/faster_rcnn/resnet_SGG_emb.py:144-177: fc6 50176->4096, fc7,
+// fc8, so_vis_embeddings, fc_so, fc_lov, fc_fusion, fc_rel; FC = nn.Linear + optional ReLU, lib/model/utils/network.py).
+// x is K-major (rows of activations), W is nn.Linear's [out, in] layout, i.e. K-major as well.
+//
+// One CTA computes one 128 x 256 output tile:
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the x tile (128 rows) and the W tile (256 rows), one
+//               128-byte swizzled k-block (64 bf16 / 32 tf32) per pipeline stage, completion on an mbarrier;
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=32 bytes per instruction) straight
+//               from the swizzled shared-memory tiles; the fp32 accumulator lives in tensor memory (256 columns);
+//               tcgen05.commit hands each stage back to the producer and finally signals the epilogue;
+//   warps 2-5   epilogue: tcgen05.ld of the accumulator (lane = tile row), + bias, ReLU, fp32 or bf16 stores.
+// Operands are bf16 (kind::f16) or fp32 consumed as tf32 (kind::tf32); accumulation is fp32 in both.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace i2v {
+namespace {
+
+constexpr int kBM = 128, kBN = 256, kStages = 4;
+constexpr int kRowBytes = 128;                    // one swizzle row of a k-block
+constexpr int kABytes = kBM * kRowBytes;          // 16 KB
+constexpr int kBBytes = kBN * kRowBytes;          // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major tile stored as 128-byte rows with the 128B swizzle (what the TMA
+// wrote): 8-row groups are 1024 bytes apart (SBO), the leading-dimension offset is unused for swizzled K-major
+// tiles, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// KIND 0: bf16 operands (64 elements per k-block), KIND 1: fp32 operands read as tf32 (32 elements per k-block).
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+    linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                          const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
+                          int y_bf16, int relu) {
+    constexpr int ELEMS = (KIND == 0) ? 64 : 32;
+    // instruction descriptor: D = fp32, A/B format (1 = bf16 under kind::f16, 2 = tf32), both K-major, N >> 3, M >> 4
+    constexpr uint32_t FMT = (KIND == 0) ? 1u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+    extern __shared__ uint8_t raw_smem[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* accum = empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+    const int kblocks = (K + ELEMS - 1) / ELEMS;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // tensor memory for the 128 x 256 fp32 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                const unsigned round = (unsigned)(kb / kStages);
+                mbar_wait(empty + s, (round & 1u) ^ 1u);
+                mbar_expect_tx(full + s, kStageBytes);
+                uint8_t* a = smem + (size_t)s * kStageBytes;
+                tma_load_2d(a, &map_x, kb * ELEMS, m0, full + s);
+                tma_load_2d(a + kABytes, &map_w, kb * ELEMS, n0, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                const unsigned round = (unsigned)(kb / kStages);
+                mbar_wait(full + s, round & 1u);
+                tc_fence_after();
+                const uint32_t a = smem_u32(smem + (size_t)s * kStageBytes);
+                const uint64_t adesc = umma_desc(a), bdesc = umma_desc(a + kABytes);
+#pragma unroll
+                for (int k = 0; k < kRowBytes / 32; ++k) {
+                    // +32 bytes along K inside the swizzle row = +2 in the 16-byte units of the descriptor
+                    umma<KIND>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                               (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(empty + s);   // the stage is free once these MMAs have read it
+            }
+            tc_commit(accum);           // all MMAs done: the accumulator is complete
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) = tile rows ----
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        const bool vec_ok = y_bf16 ? ((ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
+                                   : ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll 1
+        for (int ch = 0; ch < kBN / 32; ++ch) {
+            const int col0 = n0 + ch * 32;
+            if (col0 >= N) break;                      // uniform
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+            if (row < M) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(v[j]);
+                    if (bias != nullptr && col0 + j < N) t += __ldg(bias + col0 + j);
+                    f[j] = relu ? fmaxf(t, 0.f) : t;
+                }
+                if (y_bf16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * ldy + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(y) + (size_t)row * ldy + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = f[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- small kernels
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        int64_t rows, int64_t cols, int64_t lds, int64_t ldd) {
+    int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+    }
+}
+
+// resnet_SGG_emb.py:207-219: scores = softmax(normalize(x) . normalize(prd)^T) (softmax only when `apply_softmax`).
+// F.normalize divides by max(||v||_2, 1e-12).  One warp per row of x; the predicate embeddings are normalised by the
+// first kernel.  Plain fp32 CUDA-core arithmetic: P x R x E = 4032 x 132 x 300 is 0.3 GFLOP.
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                int rows, int cols) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = src + (size_t)row * cols;
+    float acc = 0.f;
+    for (int i = lane; i < cols; i += 32) acc += s[i] * s[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+    for (int i = lane; i < cols; i += 32) dst[(size_t)row * cols + i] = s[i] * inv;
+}
+
+constexpr int kScoreWarps = 8;
+__global__ void __launch_bounds__(kScoreWarps * 32)
+    rel_score_kernel(const float* __restrict__ x, const float* __restrict__ prdn, float* __restrict__ scores, int P, int R,
+                     int E, int apply_softmax) {
+    extern __shared__ float sc_smem[];   // [warps][E] normalised x row, [warps][R] similarities
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int row = blockIdx.x * kScoreWarps + warp;
+    if (row >= P) return;
+    float* xs = sc_smem + (size_t)warp * E;
+    float* sim = sc_smem + (size_t)kScoreWarps * E + (size_t)warp * R;
+    const float* xr = x + (size_t)row * E;
+    float acc = 0.f;
+    for (int i = lane; i < E; i += 32) {
+        float v = xr[i];
+        xs[i] = v;
+        acc += v * v;
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+    __syncwarp();
+    for (int r = 0; r < R; ++r) {
+        const float* p = prdn + (size_t)r * E;
+        float d = 0.f;
+        for (int i = lane; i < E; i += 32) d += (xs[i] * inv) * __ldg(p + i);
+        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) sim[r] = d;
+    }
+    __syncwarp();
+    float* out = scores + (size_t)row * R;
+    if (!apply_softmax) {
+        for (int r = lane; r < R; r += 32) out[r] = sim[r];
+        return;
+    }
+    float mx = -INFINITY;
+    for (int r = lane; r < R; r += 32) mx = fmaxf(mx, sim[r]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int r = lane; r < R; r += 32) {
+        float e = expf(sim[r] - mx);
+        sim[r] = e;
+        sum += e;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int r = lane; r < R; r += 32) out[r] = sim[r] / sum;
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, cols] K-major matrix with `ld` elements between rows; box = one 128-byte k-block x `box_rows` rows.
+int make_map(CUtensorMap* map, const void* base, int kind, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error("linear_forward: cuTensorMapEncodeTiled is not available from this driver");
+        return I2V_ERR_CUDA;
+    }
+    const size_t esz = kind == 0 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("linear_forward: cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] matrix, ld %lld", (int)r,
+                  (long long)rows, (long long)cols, (long long)ld);
+        return I2V_ERR_INVALID;
+    }
+    return I2V_OK;
+}
+
+}  // namespace
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                                  long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
+                                  cudaStream_t stream) {
+    I2V_REQUIRE(M >= 0 && N >= 0 && K >= 1, "linear_forward: bad shape %d x %d x %d", M, N, K);
+    I2V_REQUIRE(in_dtype == I2V_DT_BF16 || in_dtype == I2V_DT_TF32, "linear_forward: in_dtype %d", in_dtype);
+    I2V_REQUIRE(out_dtype == I2V_DT_BF16 || out_dtype == I2V_DT_F32, "linear_forward: out_dtype %d", out_dtype);
+    if (M == 0 || N == 0) return I2V_OK;
+    I2V_REQUIRE(x && w && y, "linear_forward: null pointer");
+    const int kind = in_dtype == I2V_DT_BF16 ? 0 : 1;
+    const size_t esz = kind == 0 ? 2 : 4;
+    I2V_REQUIRE(ldx >= K && ldw >= K && ldy >= N, "linear_forward: leading dimension smaller than the row");
+    I2V_REQUIRE((ldx * esz) % 16 == 0 && (ldw * esz) % 16 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0,
+                "linear_forward: x and W need 16-byte aligned bases and row pitches (TMA)");
+    alignas(64) CUtensorMap map_x, map_w;
+    I2V_TRY(make_map(&map_x, x, kind, M, K, ldx, kBM));
+    I2V_TRY(make_map(&map_w, w, kind, N, K, ldw, kBN));
+    dim3 grid((unsigned)ceil_div(N, kBN), (unsigned)ceil_div(M, kBM));
+    if (kind == 0) {
+        auto kern = linear_tcgen05_kernel<0>;
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        kern<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, out_dtype == I2V_DT_BF16, relu);
+    } else {
+        auto kern = linear_tcgen05_kernel<1>;
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        kern<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, out_dtype == I2V_DT_BF16, relu);
+    }
+    return check_launch("linear_tcgen05_kernel");
+}
+
+extern "C" int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, long long lds, long long ldd,
+                             cudaStream_t stream) {
+    I2V_REQUIRE(rows >= 0 && cols >= 0 && lds >= cols && ldd >= cols, "cast_bf16: bad shape");
+    if (rows == 0 || cols == 0) return I2V_OK;
+    I2V_REQUIRE(src && dst, "cast_bf16: null pointer");
+    cast_bf16_kernel<<<grid_for(rows * cols, 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows,
+                                                                      cols, lds, ldd);
+    return check_launch("cast_bf16_kernel");
+}
+
+extern "C" size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim) {
+    if (num_rel < 0 || emb_dim < 0) return 0;
+    return align_up((size_t)num_rel * emb_dim * sizeof(float), 256);
+}
+
+extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, int num_pairs, int num_rel, int emb_dim,
+                              int apply_softmax, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    I2V_REQUIRE(num_pairs >= 0 && num_rel >= 1 && emb_dim >= 1, "rel_scores: bad shape");
+    if (num_pairs == 0) return I2V_OK;
+    I2V_REQUIRE(x && prd && scores, "rel_scores: null pointer");
+    size_t need = i2v_rel_scores_workspace_bytes(num_rel, emb_dim);
+    if (!workspace || workspace_bytes < need) {
+        set_error("rel_scores: workspace %zu < %zu bytes", workspace_bytes, need);
+        return I2V_ERR_WORKSPACE;
+    }
+    float* prdn = static_cast<float*>(workspace);
+    l2_normalize_rows_kernel<<<ceil_div(num_rel, 8), 256, 0, stream>>>(prd, prdn, num_rel, emb_dim);
+    I2V_TRY(check_launch("l2_normalize_rows_kernel"));
+    size_t smem = (size_t)kScoreWarps * ((size_t)emb_dim + num_rel) * sizeof(float);
+    I2V_REQUIRE(smem <= (size_t)kMaxSmemPerCta, "rel_scores: emb_dim + num_rel too large for shared memory");
+    I2V_CUDA_TRY(cudaFuncSetAttribute(rel_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rel_score_kernel<<<ceil_div(num_pairs, kScoreWarps), kScoreWarps * 32, smem, stream>>>(x, prdn, scores, num_pairs,
+                                                                                          num_rel, emb_dim, apply_softmax);
+    return check_launch("rel_score_kernel");
+}

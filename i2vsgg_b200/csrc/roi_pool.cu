@@ -10,6 +10,7 @@
 // neighbouring bins of the same plane).  Backward: scatter of each pooled gradient to its recorded arg-max cell
 // (O(N*C*P*P)) instead of the reference's O(B*C*H*W*N) scan; the cffi flavour applies the same feasibility
 // tests as roi_pooling_kernel.cu:160-183 so degenerate RoIs drop out exactly as they do there.
+#include <cuda_bf16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -118,6 +119,46 @@ __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float* __restri
             if (ph < p0 || ph >= p1 || pw < q0 || pw >= q1) continue;
             atomicAdd(grad_in + am, grad_out[idx]);
         }
+    }
+}
+
+// The pooled rows the SGG projection consumes (resnet_SGG_emb.py:144-146,158-160): the model._C RoIPool value
+// (no arg-max), flattened to [N, C*PH*PW] with row pitch `ldo`, as fp32 or rounded once to bf16 for the tensor cores.
+__device__ __forceinline__ void store_pooled(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_pooled(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) roi_pool_rows_kernel(const float* __restrict__ feat,
+                                                            const float* __restrict__ rois, OutT* __restrict__ out,
+                                                            int64_t total, int batch, int C, int H, int W, int PH,
+                                                            int PW, float scale, int64_t ldo) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int pw = (int)(idx % PW);
+        int ph = (int)((idx / PW) % PH);
+        int c = (int)((idx / ((int64_t)PW * PH)) % C);
+        int n = (int)(idx / ((int64_t)PW * PH * C));
+        const float* r = rois + (size_t)n * 5;
+        int b = (int)r[0];
+        float best = 0.f;
+        if (b >= 0 && b < batch) {
+            PoolGeom g = pool_geom(r, scale, PH, PW);
+            int hs = (int)floorf(__fmul_rn((float)ph, g.bin_h)), ws = (int)floorf(__fmul_rn((float)pw, g.bin_w));
+            int he = (int)ceilf(__fmul_rn((float)(ph + 1), g.bin_h)), we = (int)ceilf(__fmul_rn((float)(pw + 1), g.bin_w));
+            hs = clampi(hs + g.rs_h, 0, H);
+            he = clampi(he + g.rs_h, 0, H);
+            ws = clampi(ws + g.rs_w, 0, W);
+            we = clampi(we + g.rs_w, 0, W);
+            bool empty = (he <= hs) || (we <= ws);
+            best = empty ? 0.f : -FLT_MAX;
+            const float* plane = feat + ((int64_t)b * C + c) * H * W;
+            for (int h = hs; h < he; ++h)
+                for (int w = ws; w < we; ++w) {
+                    float v = __ldg(plane + h * W + w);
+                    if (v > best) best = v;
+                }
+        }
+        store_pooled(out + (int64_t)n * ldo + (idx - (int64_t)n * C * PH * PW), best);
     }
 }
 
@@ -268,6 +309,22 @@ extern "C" int i2v_roi_pool_forward(const float* features, const float* rois, fl
     else
         roi_pool_fwd_kernel<I2V_ARGMAX_PLANE><<<grid, 256, 0, stream>>>(features, rois, out, argmax, total, batch, channels, height, width, pooled_h, pooled_w, spatial_scale);
     return check_launch("roi_pool_fwd_kernel");
+}
+
+extern "C" int i2v_roi_pool_rows(const float* features, const float* rois, void* out, int batch, int channels,
+                                 int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                                 long long ldo, int out_dtype, cudaStream_t stream) {
+    I2V_TRY(pool_args_ok("roi_pool_rows", features, rois, out, batch, channels, height, width, num_rois, pooled_h, pooled_w));
+    I2V_REQUIRE(out_dtype == I2V_DT_F32 || out_dtype == I2V_DT_BF16, "roi_pool_rows: out_dtype %d", out_dtype);
+    I2V_REQUIRE(ldo >= (long long)channels * pooled_h * pooled_w, "roi_pool_rows: row pitch smaller than a row");
+    int64_t total = (int64_t)num_rois * channels * pooled_h * pooled_w;
+    if (total == 0) return I2V_OK;
+    int grid = grid_for(total, 256);
+    if (out_dtype == I2V_DT_BF16)
+        roi_pool_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(features, rois, static_cast<__nv_bfloat16*>(out), total, batch, channels, height, width, pooled_h, pooled_w, spatial_scale, ldo);
+    else
+        roi_pool_rows_kernel<float><<<grid, 256, 0, stream>>>(features, rois, static_cast<float*>(out), total, batch, channels, height, width, pooled_h, pooled_w, spatial_scale, ldo);
+    return check_launch("roi_pool_rows_kernel");
 }
 
 extern "C" int i2v_roi_pool_backward(const float* grad_out, const float* rois, const int* argmax, float* grad_in,

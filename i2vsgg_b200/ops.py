@@ -9,8 +9,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ARGMAX_FLAT, ARGMAX_PLANE, IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, POOL_AVG, POOL_MAX, POOL_NONE,
-                   check, load)
+from ._lib import (ARGMAX_FLAT, ARGMAX_PLANE, DT_BF16, DT_F32, DT_TF32, IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, POOL_AVG,
+                   POOL_MAX, POOL_NONE, check, load)
 
 _POOLS = {"none": POOL_NONE, "avg": POOL_AVG, "max": POOL_MAX, POOL_NONE: POOL_NONE, POOL_AVG: POOL_AVG,
           POOL_MAX: POOL_MAX}
@@ -245,3 +245,76 @@ def triplet_topk(rel_score, conf, classes, boxes, ixs, ixo, top_k: int = 100):
         check(lib.i2v_triplet_topk(_p(rel_score), _p(conf), _p(classes), _p(boxes), _p(ixs), _p(ixo), P, R,
                                    int(top_k), _p(rec), _p(cnt), _p(ws), ws.numel(), _stream()), "i2v_triplet_topk")
     return rec, cnt
+
+
+# --------------------------------------------------------------------------------------- SGG projection
+_TORCH_DT = {torch.float32: DT_F32, torch.bfloat16: DT_BF16}
+
+
+def roi_pool_rows(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float, dtype=torch.bfloat16, out=None):
+    """`roi_pool(fmap, boxes).view(N, -1)` (resnet_SGG_emb.py:144-146,158-160) -> [N, C*ph*pw] fp32 or bf16.
+    `out` may be a row slice of a larger matrix (the object and union rows share one GEMM)."""
+    features, rois = _f32(features, "features"), _rois5(rois)
+    B, C, H, W = features.shape
+    N, K = rois.size(0), C * pooled_h * pooled_w
+    if out is None:
+        out = torch.empty((N, K), dtype=dtype, device=features.device)
+    if out.shape != (N, K) or out.stride(1) != 1 or out.dtype not in _TORCH_DT or not out.is_cuda:
+        raise _lib.I2VError("roi_pool_rows: bad `out`")
+    with torch.cuda.device(features.device):
+        check(load().i2v_roi_pool_rows(_p(features), _p(rois), _p(out), B, C, H, W, N, pooled_h, pooled_w,
+                                       float(spatial_scale), out.stride(0), _TORCH_DT[out.dtype], _stream()),
+              "i2v_roi_pool_rows")
+    return out
+
+
+def linear(x, weight, bias=None, relu: bool = False, out=None, out_dtype=torch.float32):
+    """FC of lib/model/utils/network.py on tcgen05: act(x @ weight.T + bias).  x [M,K] and weight [N,K] are both bf16
+    (tensor cores in bf16) or both fp32 (tensor cores in tf32); rows may be strided.  `out` may be a column slice."""
+    if not (x.is_cuda and weight.is_cuda) or x.dtype != weight.dtype or x.dtype not in _TORCH_DT:
+        raise _lib.I2VError("linear: x and weight must be CUDA tensors, both bf16 or both fp32")
+    if x.dim() != 2 or weight.dim() != 2 or x.size(1) != weight.size(1) or x.stride(1) != 1 or weight.stride(1) != 1:
+        raise _lib.I2VError(f"linear: bad shapes {tuple(x.shape)} x {tuple(weight.shape)}")
+    M, K = x.shape
+    N = weight.size(0)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    if out.shape != (M, N) or out.stride(1) != 1 or out.dtype not in _TORCH_DT or not out.is_cuda:
+        raise _lib.I2VError("linear: bad `out`")
+    if bias is not None:
+        bias = _f32(bias, "bias")
+        if bias.numel() != N:
+            raise _lib.I2VError("linear: bias size")
+    in_dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_TF32
+    with torch.cuda.device(x.device):
+        check(load().i2v_linear_forward(_p(x), _p(weight), _p(bias), _p(out), M, N, K, x.stride(0), weight.stride(0),
+                                        out.stride(0), in_dt, _TORCH_DT[out.dtype], int(bool(relu)), _stream()),
+              "i2v_linear_forward")
+    return out
+
+
+def cast_bf16(src, out=None):
+    """fp32 [rows, cols] (rows may be strided) -> bf16, round to nearest even."""
+    src = src if src.dtype == torch.float32 else src.float()
+    if not src.is_cuda or src.dim() != 2 or src.stride(1) != 1:
+        raise _lib.I2VError("cast_bf16: expected a 2-d CUDA tensor with contiguous rows")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        check(load().i2v_cast_bf16(_p(src), _p(out), src.size(0), src.size(1), src.stride(0), out.stride(0),
+                                   _stream()), "i2v_cast_bf16")
+    return out
+
+
+def rel_scores(x, prd, softmax: bool = True):
+    """resnet_SGG_emb.py:207-219: softmax(normalize(x) @ normalize(prd).T) -> [P, R] fp32."""
+    x, prd = _f32(x, "x"), _f32(prd, "prd")
+    P, E = x.shape
+    R = prd.size(0)
+    out = torch.empty((P, R), dtype=torch.float32, device=x.device)
+    lib = load()
+    with torch.cuda.device(x.device):
+        ws = _workspace(lib.i2v_rel_scores_workspace_bytes(R, E), x.device)
+        check(lib.i2v_rel_scores(_p(x), _p(prd), _p(out), P, R, E, int(bool(softmax)), _p(ws), ws.numel(), _stream()),
+              "i2v_rel_scores")
+    return out

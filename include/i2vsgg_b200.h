@@ -157,6 +157,31 @@ int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* c
                      float* record_out, int* count_out, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream);
 
+/* ---- 9. Embedding projection of the SGG stage (resnet_SGG_emb.py:128-221) ---- */
+#define I2V_DT_F32 0   /* fp32 storage                                                        */
+#define I2V_DT_BF16 1  /* bf16 storage; tensor-core operands under tcgen05 kind::f16           */
+#define I2V_DT_TF32 2  /* fp32 storage consumed by the tensor cores as tf32 (kind::tf32)       */
+/* roi_pool(fmap, boxes).view(N, -1) of resnet_SGG_emb.py:144-146,158-160: the model._C RoIPool values (no
+ * arg-max) written as rows [N, C*ph*pw] with pitch ldo (elements), fp32 or rounded once to bf16. */
+int i2v_roi_pool_rows(const float* features, const float* rois, void* out, int batch, int channels, int height,
+                      int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
+                      int out_dtype, cudaStream_t stream);
+/* FC of lib/model/utils/network.py (nn.Linear + optional ReLU): y[M,N] = act(x[M,K] . W[N,K]^T + bias[N]) on
+ * tcgen05 tensor cores, fp32 accumulation in tensor memory.  in_dtype: I2V_DT_BF16 (x, W bf16) or I2V_DT_TF32
+ * (x, W fp32); out_dtype: I2V_DT_F32 or I2V_DT_BF16.  ldx/ldw/ldy are row pitches in elements (x and W need
+ * 16-byte aligned bases and pitches); bias may be NULL.  y may be a column slice of a wider buffer. */
+int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                       long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
+                       cudaStream_t stream);
+/* fp32 -> bf16 (round to nearest even) of a [rows, cols] matrix; pitches in elements. */
+int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, long long lds, long long ldd,
+                  cudaStream_t stream);
+/* resnet_SGG_emb.py:207-219: scores[P,R] = softmax_R(normalize(x[P,E]) . normalize(prd[R,E])^T); the softmax is
+ * the eval-mode branch (apply_softmax != 0).  fp32 throughout. */
+size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim);
+int i2v_rel_scores(const float* x, const float* prd, float* scores, int num_pairs, int num_rel, int emb_dim,
+                   int apply_softmax, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""GPU parity tests (B200 box): the tcgen05 FC kernel, the bf16 cast, pooled rows and the relation scores.
+
+The FC kernel is compared with a float64 product of the SAME operands (bf16 values are exact in float64, tf32 operands
+are truncated to 19 bits like the tensor core does), so the only difference left is the fp32 accumulation order:
+tolerance 2e-5 of the output scale.  Against the unrounded fp32 operands the error is the documented quantisation of
+the tensor-core input format (bf16: 2^-9 per operand)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from i2vsgg_b200 import ops
+    return ops
+
+
+def _tf32_trunc(t: torch.Tensor) -> torch.Tensor:
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _ref(x, w, bias, relu):
+    y = x.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    return torch.relu(y) if relu else y
+
+
+SHAPES = [(128, 256, 64), (128, 256, 512), (1, 8, 8), (300, 300, 600), (257, 132, 304), (4096, 512, 3136),
+          (64, 4096, 1024), (520, 768, 72)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+@pytest.mark.parametrize("relu", [False, True])
+def test_linear_bf16_matches_float64_of_same_operands(ops, m, n, k, relu):
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n * 3 + k)
+    x = torch.randn((m, k), device="cuda", generator=g).bfloat16()
+    w = (torch.randn((n, k), device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn((n,), device="cuda", generator=g)
+    y = ops.linear(x, w, b, relu=relu)
+    want = _ref(x, w, b, relu)
+    scale = float(want.abs().max()) + 1e-30
+    assert y.dtype == torch.float32 and y.shape == (m, n)
+    assert float((y.double() - want).abs().max()) <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 32), (300, 300, 600), (1000, 260, 1024)])
+def test_linear_tf32_matches_float64_of_truncated_operands(ops, m, n, k):
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    x = torch.randn((m, k), device="cuda", generator=g)
+    w = torch.randn((n, k), device="cuda", generator=g) * 0.05
+    y = ops.linear(x, w, None, relu=False)
+    want = _ref(_tf32_trunc(x), _tf32_trunc(w), None, False)
+    scale = float(want.abs().max())
+    # the tensor core may round instead of truncate the low 13 bits: allow the tf32 quantisation itself
+    full = _ref(x, w, None, False)
+    err_trunc = float((y.double() - want).abs().max())
+    err_full = float((y.double() - full).abs().max())
+    assert min(err_trunc, err_full) <= 2e-5 * scale or err_full <= 2e-3 * scale, (err_trunc, err_full, scale)
+
+
+def test_linear_bf16_output_and_column_slices(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((515, 320), device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn((256, 320), device="cuda", generator=g) * 0.05).bfloat16()
+    w2 = (torch.randn((256, 320), device="cuda", generator=g) * 0.05).bfloat16()
+    cat = torch.full((515, 768), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.linear(x, w1, None, relu=True, out=cat[:, 0:256])
+    ops.linear(x, w2, None, relu=True, out=cat[:, 512:768])
+    want1 = torch.relu(x.double() @ w1.double().t())
+    want2 = torch.relu(x.double() @ w2.double().t())
+    assert torch.all(cat[:, 256:512] == 7.0)                       # the untouched slice stays untouched
+    for got, want in ((cat[:, 0:256], want1), (cat[:, 512:768], want2)):
+        assert float((got.double() - want).abs().max()) <= 2 ** -8 * float(want.abs().max())   # one bf16 rounding
+    # strided input rows: a column slice of a wider activation matrix
+    wide = torch.randn((200, 640), device="cuda", generator=g).bfloat16()
+    y = ops.linear(wide[:, 320:640], w1, None)
+    assert float((y.double() - wide[:, 320:640].double() @ w1.double().t()).abs().max()) <= 2e-5 * float(y.abs().max())
+
+
+def test_linear_rejects_bad_arguments(ops):
+    from i2vsgg_b200._lib import I2VError
+    x = torch.zeros((4, 10), device="cuda", dtype=torch.bfloat16)      # 20-byte rows: not TMA-addressable
+    w = torch.zeros((8, 10), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(I2VError):
+        ops.linear(x, w)
+    with pytest.raises(I2VError):
+        ops.linear(torch.zeros((4, 16), device="cuda"), torch.zeros((8, 16), device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(I2VError):
+        ops.linear(torch.zeros((4, 16)), torch.zeros((8, 16)))       # CPU tensors: there is no CPU path
+
+
+def test_cast_bf16_is_round_to_nearest_even(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn((37, 1000), device="cuda", generator=g) * 100
+    assert torch.equal(ops.cast_bf16(a), a.bfloat16())
+    wide = torch.randn((16, 300), device="cuda", generator=g)
+    assert torch.equal(ops.cast_bf16(wide[:, 100:228]), wide[:, 100:228].bfloat16())
+
+
+@pytest.mark.parametrize("p,r,e", [(4032, 132, 300), (7, 5, 33), (1, 132, 300)])
+def test_rel_scores_match_torch(ops, p, r, e):
+    g = torch.Generator(device="cuda").manual_seed(p + r)
+    x = torch.randn((p, e), device="cuda", generator=g)
+    prd = torch.randn((r, e), device="cuda", generator=g)
+    x[0] = 0                                                        # F.normalize's eps branch
+    got = ops.rel_scores(x, prd, softmax=True)
+    sim = torch.nn.functional.normalize(x.double(), dim=1) @ torch.nn.functional.normalize(prd.double(), dim=1).t()
+    want = torch.softmax(sim, dim=1)
+    assert float((got.double() - want).abs().max()) <= 1e-6
+    got_raw = ops.rel_scores(x, prd, softmax=False)
+    assert float((got_raw.double() - sim).abs().max()) <= 1e-6
+
+
+def test_roi_pool_rows_equal_the_roi_pool_op(ops):
+    from i2vsgg_b200 import synth
+    from i2vsgg_b200._lib import ARGMAX_PLANE
+    feat = torch.from_numpy(synth.feature_map(3, 1, 64)).cuda()
+    rois = torch.from_numpy(synth.rois(4, 50, 1)).cuda()
+    want, _ = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16, ARGMAX_PLANE)
+    rows32 = ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16, dtype=torch.float32)
+    assert torch.equal(rows32, want.reshape(50, -1))
+    big = torch.zeros((60, 64 * 49), device="cuda", dtype=torch.bfloat16)
+    ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16, out=big[10:60])
+    assert torch.equal(big[10:60], want.reshape(50, -1).bfloat16()) and torch.all(big[:10] == 0)
