@@ -1,7 +1,7 @@
 // The dense projection of the SGG stage on the 5th-generation tensor cores of sm_100a:
 //     y[M,N] = act(x[M,K] . W[N,K]^T + bias[N])
 // which is every FC layer of vrd.forward (lib/model/faster_rcnn/resnet_SGG_emb.py:144-177: fc6 50176->4096, fc7,
-// fc8, so_vis_embeddings, fc_so, fc_lov, fc_fusion, fc_rel; FC = nn.Linear + optional ReLU, lib/model/utils/network.py).
+// fc8, so_vis_embeddings, fc_so, fc_lov, fc_fusion, fc_rel; FC = nn.Linear + optional ReLU, lib/model/faster_rcnn/utils.py:48-60).
 // x is K-major (rows of activations), W is nn.Linear's [out, in] layout, i.e. K-major as well.
 //
 // One CTA computes one 128 x 256 output tile:

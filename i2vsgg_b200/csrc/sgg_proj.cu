@@ -1,0 +1,97 @@
+// Data movement around the tensor-core FC kernel for the SGG projection (resnet_SGG_emb.py:128-221):
+//   im2col        patches of conv_lo's three convolutions (resnet_SGG_emb.py:107-110,182-185) as bf16 rows, so each
+//                 convolution is one FC launch whose output rows are already NHWC for the next layer;
+//   pair rows     cat(index_select(obj, ix1), index_select(obj, ix2)) of resnet_SGG_emb.py:150-151,169 as bf16 rows.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace i2v {
+namespace {
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// out[(n*OH + oy)*OW + ox][(ky*KW + kx)*C + c] = in[n, c, oy*stride - pad + ky, ox*stride - pad + kx] (0 outside),
+// columns [KH*KW*C, ldo) are zero-filled so the row pitch can be padded to the TMA's 16-byte rule.
+// `in` is addressed through element strides (sn, sc, sy, sx): NCHW fp32 masks and NHWC bf16 activations both fit.
+template <typename InT>
+__global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                     int64_t total, int C, int H, int W, int64_t sn, int64_t sc,
+                                                     int64_t sy, int64_t sx, int KH, int KW, int stride, int pad, int OH,
+                                                     int OW, int64_t ldo) {
+    const int K = KH * KW * C;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int col = (int)(idx % ldo);
+        int64_t row = idx / ldo;
+        float v = 0.f;
+        if (col < K) {
+            int c = col % C;
+            int kx = (col / C) % KW;
+            int ky = col / (C * KW);
+            int ox = (int)(row % OW);
+            int oy = (int)((row / OW) % OH);
+            int64_t n = row / ((int64_t)OW * OH);
+            int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = to_float(in[n * sn + c * sc + y * sy + x * sx]);
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(256) pair_rows_kernel(const float* __restrict__ obj, const int64_t* __restrict__ ixs,
+                                                        const int64_t* __restrict__ ixo, __nv_bfloat16* __restrict__ out,
+                                                        int64_t total, int num_obj, int E, int64_t ldo) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int col = (int)(idx % (2 * E));
+        int64_t p = idx / (2 * E);
+        int64_t o = col < E ? ixs[p] : ixo[p];
+        float v = (o >= 0 && o < num_obj) ? obj[o * E + (col < E ? col : col - E)] : 0.f;
+        out[p * ldo + col] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int height, int width,
+                               long long stride_n, long long stride_c, long long stride_y, long long stride_x,
+                               int kernel_h, int kernel_w, int stride, int pad, void* out, long long ldo,
+                               cudaStream_t stream) {
+    I2V_REQUIRE(n >= 0 && channels >= 1 && height >= 1 && width >= 1 && kernel_h >= 1 && kernel_w >= 1 && stride >= 1 &&
+                    pad >= 0,
+                "im2col: bad shape");
+    I2V_REQUIRE(in_dtype == I2V_DT_F32 || in_dtype == I2V_DT_BF16, "im2col: in_dtype %d", in_dtype);
+    int OH = (height + 2 * pad - kernel_h) / stride + 1, OW = (width + 2 * pad - kernel_w) / stride + 1;
+    I2V_REQUIRE(OH >= 1 && OW >= 1, "im2col: kernel larger than the padded input");
+    I2V_REQUIRE(ldo >= (long long)kernel_h * kernel_w * channels, "im2col: row pitch smaller than a patch");
+    int64_t total = (int64_t)n * OH * OW * ldo;
+    if (total == 0) return I2V_OK;
+    I2V_REQUIRE(in && out, "im2col: null pointer");
+    int grid = grid_for(total, 256, 16);
+    if (in_dtype == I2V_DT_F32)
+        im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out),
+                                                       total, channels, height, width, stride_n, stride_c, stride_y,
+                                                       stride_x, kernel_h, kernel_w, stride, pad, OH, OW, ldo);
+    else
+        im2col_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in),
+                                                               static_cast<__nv_bfloat16*>(out), total, channels, height,
+                                                               width, stride_n, stride_c, stride_y, stride_x, kernel_h,
+                                                               kernel_w, stride, pad, OH, OW, ldo);
+    return check_launch("im2col_kernel");
+}
+
+extern "C" int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,
+                                  int num_pairs, int emb_dim, long long ldo, cudaStream_t stream) {
+    I2V_REQUIRE(num_obj >= 0 && num_pairs >= 0 && emb_dim >= 1 && ldo >= 2LL * emb_dim, "pair_rows: bad shape");
+    if (num_pairs == 0) return I2V_OK;
+    I2V_REQUIRE(obj && ixs && ixo && out, "pair_rows: null pointer");
+    int64_t total = (int64_t)num_pairs * 2 * emb_dim;
+    pair_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(obj, ixs, ixo, static_cast<__nv_bfloat16*>(out), total,
+                                                               num_obj, emb_dim, ldo);
+    return check_launch("pair_rows_kernel");
+}

@@ -1,0 +1,176 @@
+"""`vrd`, the relation head of lib/model/faster_rcnn/resnet_SGG_emb.py:64-256, on the sm_100a kernels.
+
+Same constructor arguments, sub-module / parameter names (a reference checkpoint loads with `load_state_dict`) and
+`forward(fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2)` signature and return values.  What changes underneath
+(SURVEY.md section 8 a19):
+
+* the feature map stays on the device (the reference bounces it through numpy, faster_rcnn_SGG_emb.py:159 /
+  resnet_SGG_emb.py:130);
+* the object rows and the union-box rows are pooled into ONE bf16 matrix [N + P, C*7*7] and go through fc6 / fc7
+  together (same weights, resnet_SGG_emb.py:147-149 and :161-163), on tcgen05 tensor cores with fp32 accumulation;
+* the concatenations of :169-186 are never materialised separately: each branch writes its column slice of the
+  fusion input from the FC epilogue;
+* conv_lo (:107-110) is three im2col + FC launches, NHWC between layers;
+* normalize / cosine similarity / softmax (:207-219) is one small fp32 kernel; the predicate embedding MLP, which
+  depends on parameters only, is evaluated once per `prepare()` instead of once per call.
+
+Only inference (`eval()` mode) is implemented: in training mode the reference applies dropout (:148-149), which this
+forward refuses loudly instead of skipping silently.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import ops
+from ..utils.config import cfg
+from .utils import FC, Conv2d
+
+
+def _dev(x, device, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.asarray(x), device=device).to(dtype)
+
+
+class vrd(nn.Module):
+    def __init__(self, args, all_obj_vecs=None, all_prd_vecs=None, bn=False):
+        super().__init__()
+        self.args = args
+        self.n_rel = args.num_relations
+        self.n_obj = args.num_classes
+        self.emb_dim = args.emb_dim
+        self.obj_vecs = all_obj_vecs
+        self.prd_vecs = all_prd_vecs
+        # resnet_SGG_emb.py:75-80 unpickles three annotation files; they feed debugging code only
+        # (faster_rcnn_SGG_emb.py:656), so a missing file leaves the attribute at None instead of failing
+        self._so_prior = self._maybe_pickle(getattr(args, "source_so_prior_path", None), as_array=True)
+        self.source_gt_rels = self._maybe_pickle(getattr(args, "source_gt_rels_path", None))
+        self.target_gt_rels = self._maybe_pickle(getattr(args, "target_gt_rels_path", None))
+
+        self.pool_size = int(getattr(cfg, "POOLING_SIZE", 7))
+        self.spatial_scale = 1.0 / 16.0
+        self.in_channels = int(getattr(args, "vrd_in_channels", 1024))
+        hidden = int(getattr(args, "vrd_hidden", 4096))
+        self.fc6 = FC(self.in_channels * self.pool_size * self.pool_size, hidden)
+        self.fc7 = FC(hidden, hidden)
+        self.so_vis_embeddings = FC(hidden, self.emb_dim, relu=False)
+        self.fc8 = FC(hidden, 256)
+        self.criterion = torch.nn.BCEWithLogitsLoss()
+
+        n_fusion = 256
+        if args.use_obj_visual:
+            self.fc_so = FC(self.emb_dim * 2, 256)
+            n_fusion += 256
+        if args.spatial_type == 1:
+            self.fc_lov = FC(8, 256)
+            n_fusion += 256
+        elif args.spatial_type == 2:
+            self.conv_lo = nn.Sequential(Conv2d(2, 96, 5, same_padding=True, stride=2, bn=bn),
+                                         Conv2d(96, 128, 5, same_padding=True, stride=2, bn=bn),
+                                         Conv2d(128, 64, 8, same_padding=False, bn=bn))
+            self.fc_lov = FC(64, 256)
+            n_fusion += 256
+        self.n_fusion = n_fusion
+        self.fc_fusion = FC(n_fusion, 256)
+        self.fc_rel = FC(256, self.emb_dim, relu=False)
+        self.prd_sem_embeddings = nn.Sequential(nn.Linear(300, 1024), nn.LeakyReLU(0.1), nn.Linear(1024, self.emb_dim))
+        self._prd_emb = None
+
+    @staticmethod
+    def _maybe_pickle(path, as_array=False):
+        if not path or not os.path.exists(path):
+            return None
+        with open(path, "rb") as fid:
+            obj = pickle.load(fid, encoding="bytes")
+        return np.array(obj) if as_array else obj
+
+    # ------------------------------------------------------------------ parameter-only work, once per weight update
+    def prepare(self):
+        """bf16 copies of every FC / conv weight and the predicate embeddings (resnet_SGG_emb.py:203-206)."""
+        for m in self.modules():
+            if isinstance(m, (FC, Conv2d)):
+                m.prepare()
+        dev = self.fc6.fc.weight.device
+        with torch.no_grad():
+            prd = torch.as_tensor(np.asarray(self.prd_vecs, dtype=np.float32), device=dev)
+            self._prd_emb = self.prd_sem_embeddings(prd).float().contiguous()
+        return self
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2, return_numpy: bool = True):
+        if self.training:
+            raise NotImplementedError("i2vsgg_b200 vrd implements the inference path; call .eval() first "
+                                      "(training mode applies dropout, resnet_SGG_emb.py:148-149)")
+        dev = self.fc6.fc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("vrd: parameters must live on a CUDA device (there is no CPU path)")
+        if self._prd_emb is None or self._prd_emb.device != dev:
+            self.prepare()
+        fmap = _dev(fmap, dev).contiguous()
+        boxes = _dev(boxes, dev).reshape(-1, 5).contiguous()
+        rel_boxes = _dev(rel_boxes, dev).reshape(-1, 5).contiguous()
+        ix1 = _dev(ix1, dev, torch.int64).reshape(-1)
+        ix2 = _dev(ix2, dev, torch.int64).reshape(-1)
+        n_obj, n_pair = boxes.size(0), rel_boxes.size(0)
+        ps = self.pool_size
+
+        # roi_pool of objects and unions -> one bf16 matrix; fc6 / fc7 over all rows at once (:144-149, :158-163)
+        k6 = self.in_channels * ps * ps
+        pooled = torch.empty((n_obj + n_pair, k6), dtype=torch.bfloat16, device=dev)
+        ops.roi_pool_rows(fmap, boxes, ps, ps, self.spatial_scale, out=pooled[:n_obj])
+        ops.roi_pool_rows(fmap, rel_boxes, ps, ps, self.spatial_scale, out=pooled[n_obj:])
+        h = self.fc7(self.fc6(pooled))
+        obj_feature = self.so_vis_embeddings(h[:n_obj], out_dtype=torch.float32)            # :150
+
+        fusion = torch.empty((n_pair, self.n_fusion), dtype=torch.bfloat16, device=dev)
+        col = 0
+        self.fc8(h[n_obj:], out=fusion[:, col:col + 256])                                   # :164
+        col += 256
+        if self.args.use_obj_visual:                                                        # :166-170
+            self.fc_so(ops.pair_rows_bf16(obj_feature, ix1, ix2), out=fusion[:, col:col + 256])
+            col += 256
+        if self.args.spatial_type == 1:                                                     # :172-174
+            sp = _dev(SpatialFea, dev).reshape(n_pair, 8).contiguous()
+            self.fc_lov(ops.cast_bf16(sp), out=fusion[:, col:col + 256])
+            col += 256
+        elif self.args.spatial_type == 2:                                                   # :175-179
+            sp = _dev(SpatialFea, dev).reshape(n_pair, 2, 32, 32).contiguous()
+            lo = self.conv_lo[0](sp, "nchw")
+            lo = self.conv_lo[1](lo, "nhwc")
+            lo = self.conv_lo[2](lo, "nhwc")
+            self.fc_lov(lo.view(n_pair, -1), out=fusion[:, col:col + 256])
+            col += 256
+        x = self.fc_rel(self.fc_fusion(fusion), out_dtype=torch.float32)                    # :190-191
+        scores = ops.rel_scores(x, self._prd_emb, softmax=True)                             # :203-219 (eval)
+        return scores, (x.detach().cpu().numpy() if return_numpy else x)
+
+    def save_semantic_embedding(self, save_path):
+        if self._prd_emb is None:
+            self.prepare()
+        np.save(save_path, self._prd_emb.detach().cpu().numpy())
+
+    def _set_trainable(self, model, requires_grad):
+        for param in model.parameters():
+            param.requires_grad = requires_grad
+
+    # ------------------------------------------------------------------ host helpers kept for callers (:240-256)
+    def _getUnionBBox(self, aBB, bBB, ih, iw, margin=10):
+        return [max(0, min(aBB[0], bBB[0]) - margin), max(0, min(aBB[1], bBB[1]) - margin),
+                min(iw, max(aBB[2], bBB[2]) + margin), min(ih, max(aBB[3], bBB[3]) + margin)]
+
+    def _getDualMask(self, ih, iw, bb):
+        rh = 32.0 / ih
+        rw = 32.0 / iw
+        x1 = max(0, int(math.floor(bb[0] * rw)))
+        x2 = min(32, int(math.ceil(bb[2] * rw)))
+        y1 = max(0, int(math.floor(bb[1] * rh)))
+        y2 = min(32, int(math.ceil(bb[3] * rh)))
+        mask = np.zeros((32, 32))
+        mask[y1:y2, x1:x2] = 1
+        return mask

@@ -1,0 +1,76 @@
+"""`Conv2d` and `FC` of lib/model/faster_rcnn/utils.py:32-60: parameter containers with the reference's names
+(`.conv`, `.bn`, `.fc`), so a reference checkpoint loads with `load_state_dict`.  Their `forward` runs on the
+sm_100a kernels of this package: bf16 tensor-core operands, fp32 accumulation."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import ops
+
+
+class FC(nn.Module):
+    def __init__(self, in_features, out_features, relu=True):
+        super().__init__()
+        self.fc = nn.Linear(in_features, out_features)
+        self.relu = nn.ReLU(inplace=True) if relu else None
+        self._w = None
+
+    def prepare(self):
+        """(Re)builds the bf16 copy of the weight the tensor cores read; the row pitch is padded to 16 bytes."""
+        w = self.fc.weight.detach()
+        k = w.size(1)
+        kp = (k + 7) // 8 * 8
+        buf = torch.zeros((w.size(0), kp), dtype=torch.bfloat16, device=w.device)
+        ops.cast_bf16(w.float().contiguous(), buf[:, :k])
+        self._w = buf[:, :k]
+        self._b = self.fc.bias.detach().float().contiguous()
+        return self
+
+    def forward(self, x, out=None, out_dtype=torch.bfloat16):
+        """x [M, in_features] bf16 (rows may be strided) -> [M, out_features]; `out` may be a column slice."""
+        if self._w is None or self._w.device != x.device:
+            self.prepare()
+        return ops.linear(x, self._w, self._b, relu=self.relu is not None, out=out, out_dtype=out_dtype)
+
+
+class Conv2d(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, relu=True, same_padding=False, bn=False):
+        super().__init__()
+        padding = int((kernel_size - 1) / 2) if same_padding else 0
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding=padding)
+        self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0, affine=True) if bn else None
+        self.relu = nn.ReLU(inplace=True) if relu else None
+        self._w = None
+
+    def prepare(self):
+        """Weight as [out, (ky, kx, c)] bf16 rows (the patch order of `ops.im2col_bf16`), eval-mode BatchNorm folded
+        into weight and bias (utils.py:43-44 in eval mode is an affine map per output channel)."""
+        w = self.conv.weight.detach().float()
+        b = self.conv.bias.detach().float()
+        if self.bn is not None:
+            s = self.bn.weight.detach().float() / torch.sqrt(self.bn.running_var.float() + self.bn.eps)
+            w = w * s[:, None, None, None]
+            b = (b - self.bn.running_mean.float()) * s + self.bn.bias.detach().float()
+        o, c, kh, kw = w.shape
+        k = kh * kw * c
+        kp = (k + 7) // 8 * 8
+        buf = torch.zeros((o, kp), dtype=torch.bfloat16, device=w.device)
+        ops.cast_bf16(w.permute(0, 2, 3, 1).reshape(o, k).contiguous(), buf[:, :k])
+        self._w, self._kp = buf, kp
+        self._b = b.contiguous()
+        return self
+
+    def forward(self, x, layout: str):
+        """x [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`'nhwc'`) -> NHWC bf16 [N,OH,OW,out]: im2col rows + one FC launch."""
+        if self._w is None or self._w.device != x.device:
+            self.prepare()
+        kh = self.conv.kernel_size[0]
+        if (layout == "nhwc" and x.dtype == torch.bfloat16 and x.size(1) == kh and x.size(2) == kh
+                and self.conv.padding[0] == 0 and self._kp == kh * kh * x.size(3) and x.is_contiguous()):
+            # the kernel covers the whole map: the NHWC activation row already is the (ky, kx, c) patch
+            patches, (n, oh, ow) = x.view(x.size(0), -1), (x.size(0), 1, 1)
+        else:
+            patches, (n, oh, ow) = ops.im2col_bf16(x, kh, self.conv.stride[0], self.conv.padding[0], layout, ld=self._kp)
+        y = ops.linear(patches, self._w, self._b, relu=self.relu is not None, out_dtype=torch.bfloat16)
+        return y.view(n, oh, ow, -1)

@@ -269,7 +269,7 @@ def roi_pool_rows(features, rois, pooled_h: int, pooled_w: int, spatial_scale: f
 
 
 def linear(x, weight, bias=None, relu: bool = False, out=None, out_dtype=torch.float32):
-    """FC of lib/model/utils/network.py on tcgen05: act(x @ weight.T + bias).  x [M,K] and weight [N,K] are both bf16
+    """FC of lib/model/faster_rcnn/utils.py:48-60 on tcgen05: act(x @ weight.T + bias).  x [M,K] and weight [N,K] are both bf16
     (tensor cores in bf16) or both fp32 (tensor cores in tf32); rows may be strided.  `out` may be a column slice."""
     if not (x.is_cuda and weight.is_cuda) or x.dtype != weight.dtype or x.dtype not in _TORCH_DT:
         raise _lib.I2VError("linear: x and weight must be CUDA tensors, both bf16 or both fp32")
@@ -317,4 +317,43 @@ def rel_scores(x, prd, softmax: bool = True):
         ws = _workspace(lib.i2v_rel_scores_workspace_bytes(R, E), x.device)
         check(lib.i2v_rel_scores(_p(x), _p(prd), _p(out), P, R, E, int(bool(softmax)), _p(ws), ws.numel(), _stream()),
               "i2v_rel_scores")
+    return out
+
+
+def im2col_bf16(x, kernel: int, stride: int, pad: int, layout: str, ld: int | None = None):
+    """Patches of a square-kernel convolution as bf16 rows [(n, oy, ox), (ky, kx, c)] (pitch `ld`, zero padded).
+    x is [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`layout='nhwc'`), fp32 or bf16, contiguous."""
+    if not x.is_cuda or x.dim() != 4 or x.dtype not in _TORCH_DT or not x.is_contiguous():
+        raise _lib.I2VError("im2col_bf16: expected a contiguous 4-d fp32/bf16 CUDA tensor")
+    if layout == "nchw":
+        n, c, h, w = x.shape
+        sn, sc, sy, sx = c * h * w, h * w, w, 1
+    elif layout == "nhwc":
+        n, h, w, c = x.shape
+        sn, sc, sy, sx = h * w * c, 1, w * c, c
+    else:
+        raise _lib.I2VError("im2col_bf16: layout must be nchw or nhwc")
+    oh, ow = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
+    k = kernel * kernel * c
+    ld = k if ld is None else int(ld)
+    out = torch.empty((n * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().i2v_im2col_bf16(_p(x), _TORCH_DT[x.dtype], n, c, h, w, sn, sc, sy, sx, kernel, kernel, stride, pad,
+                                     _p(out), ld, _stream()), "i2v_im2col_bf16")
+    return out, (n, oh, ow)
+
+
+def pair_rows_bf16(obj, ixs, ixo, out=None):
+    """cat(obj[ixs], obj[ixo], dim=1) as bf16 rows [P, 2E] (resnet_SGG_emb.py:150-151,169)."""
+    obj = _f32(obj, "obj")
+    ixs, ixo = ixs.long().contiguous(), ixo.long().contiguous()
+    N, E = obj.shape
+    P = ixs.numel()
+    if out is None:
+        out = torch.empty((P, 2 * E), dtype=torch.bfloat16, device=obj.device)
+    if out.shape != (P, 2 * E) or out.stride(1) != 1 or out.dtype != torch.bfloat16:
+        raise _lib.I2VError("pair_rows_bf16: bad `out`")
+    with torch.cuda.device(obj.device):
+        check(load().i2v_pair_rows_bf16(_p(obj), _p(ixs), _p(ixo), _p(out), N, P, E, out.stride(0), _stream()),
+              "i2v_pair_rows_bf16")
     return out

@@ -158,3 +158,60 @@ def clip_detections(seed: int, frames: int, num: int = 64, sigma: float = 4.0):
     boxes[:, :, 0::2] = np.clip(boxes[:, :, 0::2] + steps[:, :, 0:1], 0, IM_W - 1)
     boxes[:, :, 1::2] = np.clip(boxes[:, :, 1::2] + steps[:, :, 1:2], 0, IM_H - 1)
     return boxes, classes, conf
+
+
+# ------------------------------------------------------------------------------------------------ SGG projection
+class VrdArgs:
+    """The attributes of the reference's argparse namespace that `vrd` reads (parser_func.py:137-184)."""
+
+    def __init__(self, num_classes=35, num_relations=132, emb_dim=300, use_obj_visual=True, spatial_type=2,
+                 vrd_in_channels=1024, vrd_hidden=4096):
+        self.num_classes, self.num_relations, self.emb_dim = num_classes, num_relations, emb_dim
+        self.use_obj_visual, self.spatial_type = use_obj_visual, spatial_type
+        self.vrd_in_channels, self.vrd_hidden = vrd_in_channels, vrd_hidden   # read by i2vsgg_b200 only (small tests)
+        self.source_so_prior_path = self.source_gt_rels_path = self.target_gt_rels_path = None
+
+
+def vrd_params(seed: int = 1234, args: VrdArgs | None = None, pool: int = 7) -> dict:
+    """Random-init parameters of `vrd` keyed like its state_dict (resnet_SGG_emb.py:83-127), fp32.
+    Weights ~ N(0, 2/fan_in) so activations keep unit scale through the stack, biases ~ N(0, 0.1)."""
+    a = args or VrdArgs()
+    rng = np.random.default_rng(seed)
+    p = {}
+
+    def lin(name, fin, fout):
+        p[name + ".weight"] = (rng.standard_normal((fout, fin), dtype=np.float32) * np.float32(np.sqrt(2.0 / fin)))
+        p[name + ".bias"] = rng.standard_normal((fout,), dtype=np.float32) * np.float32(0.1)
+
+    def conv(name, cin, cout, k):
+        p[name + ".weight"] = (rng.standard_normal((cout, cin, k, k), dtype=np.float32) *
+                               np.float32(np.sqrt(2.0 / (cin * k * k))))
+        p[name + ".bias"] = rng.standard_normal((cout,), dtype=np.float32) * np.float32(0.1)
+
+    lin("fc6.fc", a.vrd_in_channels * pool * pool, a.vrd_hidden)
+    lin("fc7.fc", a.vrd_hidden, a.vrd_hidden)
+    lin("so_vis_embeddings.fc", a.vrd_hidden, a.emb_dim)
+    lin("fc8.fc", a.vrd_hidden, 256)
+    n_fusion = 256
+    if a.use_obj_visual:
+        lin("fc_so.fc", a.emb_dim * 2, 256)
+        n_fusion += 256
+    if a.spatial_type == 1:
+        lin("fc_lov.fc", 8, 256)
+        n_fusion += 256
+    elif a.spatial_type == 2:
+        conv("conv_lo.0.conv", 2, 96, 5)
+        conv("conv_lo.1.conv", 96, 128, 5)
+        conv("conv_lo.2.conv", 128, 64, 8)
+        lin("fc_lov.fc", 64, 256)
+        n_fusion += 256
+    lin("fc_fusion.fc", n_fusion, 256)
+    lin("fc_rel.fc", 256, a.emb_dim)
+    lin("prd_sem_embeddings.0", 300, 1024)
+    lin("prd_sem_embeddings.2", 1024, a.emb_dim)
+    return p
+
+
+def prd_vectors(seed: int, num_relations: int = 132) -> np.ndarray:
+    """GloVe stand-in [n_rel, 300] ~ N(0,1)."""
+    return np.random.default_rng(seed).standard_normal((num_relations, 300), dtype=np.float32)

@@ -166,7 +166,7 @@ int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* c
 int i2v_roi_pool_rows(const float* features, const float* rois, void* out, int batch, int channels, int height,
                       int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
                       int out_dtype, cudaStream_t stream);
-/* FC of lib/model/utils/network.py (nn.Linear + optional ReLU): y[M,N] = act(x[M,K] . W[N,K]^T + bias[N]) on
+/* FC of lib/model/faster_rcnn/utils.py:48-60 (nn.Linear + optional ReLU): y[M,N] = act(x[M,K] . W[N,K]^T + bias[N]) on
  * tcgen05 tensor cores, fp32 accumulation in tensor memory.  in_dtype: I2V_DT_BF16 (x, W bf16) or I2V_DT_TF32
  * (x, W fp32); out_dtype: I2V_DT_F32 or I2V_DT_BF16.  ldx/ldw/ldy are row pitches in elements (x and W need
  * 16-byte aligned bases and pitches); bias may be NULL.  y may be a column slice of a wider buffer. */
@@ -176,6 +176,16 @@ int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y,
 /* fp32 -> bf16 (round to nearest even) of a [rows, cols] matrix; pitches in elements. */
 int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, long long lds, long long ldd,
                   cudaStream_t stream);
+/* Patches of a convolution as bf16 rows (conv_lo, resnet_SGG_emb.py:107-110,182-185 -> one FC launch per layer):
+ * out[(n*OH+oy)*OW+ox][(ky*KW+kx)*C+c] = in[n,c,oy*stride-pad+ky,ox*stride-pad+kx], zero outside and in the
+ * pitch padding [KH*KW*C, ldo).  `in` (fp32 or bf16) is addressed by element strides, so NCHW and NHWC both fit. */
+int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int height, int width, long long stride_n,
+                    long long stride_c, long long stride_y, long long stride_x, int kernel_h, int kernel_w,
+                    int stride, int pad, void* out, long long ldo, cudaStream_t stream);
+/* cat(index_select(obj, 0, ixs), index_select(obj, 0, ixo), 1) of resnet_SGG_emb.py:150-151,169 as bf16 rows
+ * [P, 2E] with pitch ldo; obj [N,E] fp32, ixs/ixo [P] int64. */
+int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,
+                       int num_pairs, int emb_dim, long long ldo, cudaStream_t stream);
 /* resnet_SGG_emb.py:207-219: scores[P,R] = softmax_R(normalize(x[P,E]) . normalize(prd[R,E])^T); the softmax is
  * the eval-mode branch (apply_softmax != 0).  fp32 throughout. */
 size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim);

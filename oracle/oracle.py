@@ -303,3 +303,67 @@ def detection_output(rel_score, confs, classes, boxes, ixs, ixo, top: int = 100)
     classes = np.asarray(classes)
     labels = np.stack([classes[ixs[pair]], rel, classes[ixo[pair]]], axis=1).astype(np.float32)
     return prob[pair, rel], labels, boxes[ixs[pair]], boxes[ixo[pair]], pair.astype(np.int64)
+
+
+# ------------------------------------------------------------------ SGG projection (resnet_SGG_emb.py:128-221)
+def _fc(x, params, name, relu=True):
+    """FC of lib/model/faster_rcnn/utils.py:48-60: nn.Linear then optional ReLU, fp32."""
+    y = x.astype(np.float32) @ params[name + ".weight"].T + params[name + ".bias"]
+    return np.maximum(y, 0, out=y) if relu else y
+
+
+def _conv2d(x, w, b, stride: int, pad: int, relu=True):
+    """nn.Conv2d + ReLU of lib/model/faster_rcnn/utils.py:32-46 (bn=False), NCHW fp32, by explicit patches."""
+    n, c, h, wd = x.shape
+    o, _, kh, kw = w.shape
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    oh, ow = (h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kw) // stride + 1
+    s = xp.strides
+    patches = np.lib.stride_tricks.as_strided(xp, (n, oh, ow, c, kh, kw),
+                                              (s[0], s[2] * stride, s[3] * stride, s[1], s[2], s[3]))
+    y = patches.reshape(n * oh * ow, c * kh * kw).astype(np.float32) @ w.reshape(o, -1).T + b
+    y = y.reshape(n, oh, ow, o).transpose(0, 3, 1, 2)
+    return np.maximum(y, 0) if relu else y
+
+
+def _normalize(x):
+    """F.normalize(p=2, dim=1): x / max(||x||, 1e-12)."""
+    return x / np.maximum(np.sqrt((x.astype(np.float64) ** 2).sum(1, keepdims=True)), 1e-12).astype(np.float32)
+
+
+def vrd_forward(params: dict, prd_vecs, fmap, boxes, rel_boxes, spatial, ix1, ix2, use_obj_visual=True,
+                spatial_type=2, pool: int = 7, rows=None, nthreads: int = 1):
+    """vrd.forward in eval mode (resnet_SGG_emb.py:128-221) restated in numpy fp32 -> (scores [P,n_rel], feat [P,emb]).
+
+    roi_pool is the model._C flavour (`c_roi_pool_forward`); dropout is the identity in eval mode (:148-149).
+    `rows` restricts the computation to a subset of pair indices (full-size spot checks)."""
+    fmap = _f32(fmap)
+    boxes = _f32(boxes).reshape(-1, 5)
+    rel_boxes = _f32(rel_boxes).reshape(-1, 5)
+    ix1, ix2 = np.asarray(ix1, np.int64), np.asarray(ix2, np.int64)
+    spatial = _f32(spatial)
+    if rows is not None:
+        rows = np.asarray(rows, np.int64)
+        rel_boxes, ix1, ix2, spatial = rel_boxes[rows], ix1[rows], ix2[rows], spatial[rows]
+    x_so, _ = c_roi_pool_forward(fmap, boxes, pool, pool, 1.0 / 16, nthreads)                    # :144
+    x_so = _fc(_fc(x_so.reshape(len(boxes), -1), params, "fc6.fc"), params, "fc7.fc")           # :146-149
+    obj = _fc(x_so, params, "so_vis_embeddings.fc", relu=False)                                 # :150
+    x_u, _ = c_roi_pool_forward(fmap, rel_boxes, pool, pool, 1.0 / 16, nthreads)                 # :158
+    x = _fc(_fc(_fc(x_u.reshape(len(rel_boxes), -1), params, "fc6.fc"), params, "fc7.fc"), params, "fc8.fc")  # :160-164
+    parts = [x]
+    if use_obj_visual:                                                                          # :166-170
+        parts.append(_fc(np.concatenate([obj[ix1], obj[ix2]], 1), params, "fc_so.fc"))
+    if spatial_type == 1:                                                                       # :172-174
+        parts.append(_fc(spatial.reshape(len(rel_boxes), 8), params, "fc_lov.fc"))
+    elif spatial_type == 2:                                                                     # :175-179
+        lo = _conv2d(spatial.reshape(-1, 2, 32, 32), params["conv_lo.0.conv.weight"], params["conv_lo.0.conv.bias"], 2, 2)
+        lo = _conv2d(lo, params["conv_lo.1.conv.weight"], params["conv_lo.1.conv.bias"], 2, 2)
+        lo = _conv2d(lo, params["conv_lo.2.conv.weight"], params["conv_lo.2.conv.bias"], 1, 0)
+        parts.append(_fc(lo.reshape(len(rel_boxes), -1), params, "fc_lov.fc"))
+    x = _fc(_fc(np.concatenate(parts, 1), params, "fc_fusion.fc"), params, "fc_rel.fc", relu=False)  # :190-191
+    prd = _f32(prd_vecs) @ params["prd_sem_embeddings.0.weight"].T + params["prd_sem_embeddings.0.bias"]   # :203-206
+    prd = np.where(prd > 0, prd, np.float32(0.1) * prd)
+    prd = prd @ params["prd_sem_embeddings.2.weight"].T + params["prd_sem_embeddings.2.bias"]
+    sim = (_normalize(x) @ _normalize(prd).T).astype(np.float64)                                # :207-211
+    e = np.exp(sim - sim.max(1, keepdims=True))                                                 # :216-219 (eval)
+    return (e / e.sum(1, keepdims=True)).astype(np.float32), x

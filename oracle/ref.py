@@ -243,3 +243,61 @@ def py_bbox_transform_inv_clip(anchors, deltas, im_info):
     B = deltas.shape[0]
     p = bbox_transform_inv(torch.from_numpy(anchors), torch.from_numpy(deltas), B)
     return clip_boxes(p, torch.from_numpy(im_info), B).numpy()
+
+
+def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial, classes, ix1, ix2):
+    """Executes `vrd.forward` (lib/model/faster_rcnn/resnet_SGG_emb.py:128-221) UNMODIFIED on the CPU.
+
+    What is stubbed, and only that: `model._C` has no source in the reference (lib/setup.py:19), so
+    `model.roi_layers.ROIPool` is bound to torchvision.ops.roi_pool (the same maskrcnn-benchmark op); the detector base
+    class `_fasterRCNN` (not on this path) is an empty nn.Module; `.cuda()` is the identity because the build container
+    has no GPU; the three annotation pickles the constructor opens (:75-80) are empty temporaries.
+    `params` maps the reference's state_dict keys to numpy arrays.  Returns (scores [P,n_rel], feat [P,emb])."""
+    _py_setup()
+    import pickle
+    import tempfile
+    import torch
+    import torchvision
+    from torch import nn
+
+    if "model.roi_layers" not in sys.modules or not getattr(sys.modules["model.roi_layers"], "_i2v_stub", False):
+        rl = types.ModuleType("model.roi_layers")
+        rl._i2v_stub = True
+
+        class ROIPool(nn.Module):
+            def __init__(self, output_size, spatial_scale):
+                super().__init__()
+                self.output_size, self.spatial_scale = output_size, spatial_scale
+
+            def forward(self, input, rois):
+                return torchvision.ops.roi_pool(input, rois, self.output_size, self.spatial_scale)
+
+        rl.ROIPool = ROIPool
+        rl.ROIAlign = None
+        sys.modules["model.roi_layers"] = rl
+        fr = types.ModuleType("model.faster_rcnn.faster_rcnn_SGG_emb")
+        fr._fasterRCNN = type("_fasterRCNN", (nn.Module,), {})
+        sys.modules["model.faster_rcnn.faster_rcnn_SGG_emb"] = fr
+    from model.faster_rcnn import resnet_SGG_emb as ref_mod
+
+    tmp = tempfile.mkdtemp()
+    for name in ("source_so_prior_path", "source_gt_rels_path", "target_gt_rels_path"):
+        path = os.path.join(tmp, name + ".pkl")
+        with open(path, "wb") as f:
+            pickle.dump([], f)
+        setattr(args, name, path)
+    old_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        net = ref_mod.vrd(args, None, np.asarray(prd_vecs, np.float32))
+        sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()}
+        missing = net.load_state_dict(sd, strict=True)
+        net.eval()
+        net.obj_vecs = np.zeros((args.num_classes + 1, 300), np.float32)
+        with torch.no_grad():
+            scores, feat = net(np.asarray(fmap, np.float32), np.asarray(boxes, np.float32),
+                               np.asarray(rel_boxes, np.float32), np.asarray(spatial, np.float32),
+                               list(classes), np.asarray(ix1), np.asarray(ix2))
+    finally:
+        torch.Tensor.cuda = old_cuda
+    return scores.numpy(), feat
