@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(256) c_roi_align_bwd_kernel(const float* __res
     }
 }
 
+int roi_pool_rows_plane(const float* features, const float* rois, void* out, int batch, int channels, int height,
+                        int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
+                        int out_dtype, cudaStream_t stream);  // roi_pool_plane.cu
+
 static int pool_args_ok(const char* who, const void* a, const void* b, const void* c, int batch, int channels,
                         int height, int width, int num_rois, int ph, int pw) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0 && height >= 1 && width >= 1 && ph >= 1 && pw >= 1,
@@ -319,6 +323,9 @@ extern "C" int i2v_roi_pool_rows(const float* features, const float* rois, void*
     I2V_REQUIRE(ldo >= (long long)channels * pooled_h * pooled_w, "roi_pool_rows: row pitch smaller than a row");
     int64_t total = (int64_t)num_rois * channels * pooled_h * pooled_w;
     if (total == 0) return I2V_OK;
+    int rc = roi_pool_rows_plane(features, rois, out, batch, channels, height, width, num_rois, pooled_h, pooled_w,
+                                 spatial_scale, ldo, out_dtype, stream);
+    if (rc != I2V_ERR_UNSUPPORTED) return rc;   // otherwise: shapes the plane kernel does not take
     int grid = grid_for(total, 256);
     if (out_dtype == I2V_DT_BF16)
         roi_pool_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(features, rois, static_cast<__nv_bfloat16*>(out), total, batch, channels, height, width, pooled_h, pooled_w, spatial_scale, ldo);

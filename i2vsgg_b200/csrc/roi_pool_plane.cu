@@ -1,0 +1,159 @@
+// Plane-resident RoIPool rows for the SGG projection (resnet_SGG_emb.py:144-146,158-160): 4032 union boxes pool the
+// SAME frame, so the 16 feature planes of a CTA are copied from HBM/L2 into shared memory once and every bin maximum is
+// taken from there.
+//
+//   * planes as [row][65 columns][16 channels] fp32: lanes are channels, a half-warp reads one 64-byte cell; with the odd
+//     row pitch the bank half of a cell is (row + column) mod 2, so the two half-warps -- which scan the even and the odd
+//     rows of the same bin, same column -- never collide: every shared load is conflict free by construction;
+//   * one warp per RoI at a time: bin bounds are computed once per RoI by 14 lanes (roi_pooling_kernel.cu:44-66
+//     arithmetic, the model._C flavour has the same rounding) and broadcast with shuffles;
+//   * the 16 x 49 results of a (RoI, channel tile) are contiguous in the [N, C*49] output row: they are staged in shared
+//     memory and leave as one TMA bulk store (1568 bytes in bf16, 3136 in fp32).
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace i2v {
+namespace {
+
+constexpr int kK = 16;            // channels per CTA
+constexpr int kPitch = 65;        // cells per shared-memory row (odd: see above)
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBins = 49;
+
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void put(float* p, float v) { *p = v; }
+__device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+    roi_pool_plane_kernel(const float* __restrict__ feat, const float* __restrict__ rois, OutT* __restrict__ out,
+                          int batch, int C, int H, int W, int num_rois, float scale, int64_t ldo, int split) {
+    extern __shared__ __align__(128) float smem[];
+    float* planes = smem;                                             // [H][65][16]
+    OutT* stage = reinterpret_cast<OutT*>(smem + (size_t)H * kPitch * kK);   // [warps][16][49]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctiles = C / kK;
+    const int s = blockIdx.x % split;
+    const int ct = (blockIdx.x / split) % ctiles;
+    const int b = blockIdx.x / (split * ctiles);
+
+    // ---- fill: global [c][row][col] -> shared [row][col][16]; a warp-wide 4-byte cp.async writes two adjacent cells x
+    // 16 channels = 128 contiguous shared bytes; everything is in flight before the single wait ----
+    {
+        const int HW = H * W;
+        const int tc = lane & 15, tdx = lane >> 4;
+        const float* src = feat + ((size_t)b * C + (size_t)ct * kK + tc) * HW + tdx;
+        float* dst = planes + tdx * kK + tc;
+        for (int row = warp; row < H; row += kWarps) {
+            const float* g = src + row * W;
+            float* d = dst + (size_t)row * kPitch * kK;
+            for (int j = 0; 2 * j < W; ++j)
+                if (2 * j + tdx < W) cp_async4(d + j * 2 * kK, g + 2 * j);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+
+    const int half = lane >> 4, c = lane & 15;
+    OutT* my_stage = stage + (size_t)warp * kK * kBins;
+    const float* lane_base = planes + c;
+    for (int n = s * kWarps + warp; n < num_rois; n += split * kWarps) {
+        const float* r = rois + (size_t)n * 5;
+        const int rb = (int)__ldg(r);
+        const bool mine = (rb == b);
+        const bool stray = (b == 0) && (rb < 0 || rb >= batch);     // out-of-range frame index: a zero row
+        if (!mine && !stray) continue;                               // uniform per warp
+        // ---- bin bounds: lanes 0-6 hold (hstart, hend) of bin row `lane`, lanes 7-13 (wstart, wend) of bin column ----
+        int lo = 0, hi = 0;
+        {
+            const int axis = lane >= 7;                   // 0: rows (y), 1: columns (x)
+            const int p = axis ? lane - 7 : lane;
+            const float a0 = __ldg(r + (axis ? 1 : 2)), a1 = __ldg(r + (axis ? 3 : 4));
+            const int rs = (int)roundf(__fmul_rn(a0, scale)), re = (int)roundf(__fmul_rn(a1, scale));
+            const int extent = max(re - rs + 1, 1);
+            const float bin = __fdiv_rn((float)extent, 7.f);
+            const int lim = axis ? W : H;
+            lo = min(max((int)floorf(__fmul_rn((float)p, bin)) + rs, 0), lim);
+            hi = min(max((int)ceilf(__fmul_rn((float)(p + 1), bin)) + rs, 0), lim);
+        }
+        // the previous tile of this warp must have left the staging buffer
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (mine) {
+#pragma unroll 1
+            for (int ph = 0; ph < 7; ++ph) {
+                const int hs = __shfl_sync(0xffffffffu, lo, ph), he = __shfl_sync(0xffffffffu, hi, ph);
+#pragma unroll 1
+                for (int pw = 0; pw < 7; ++pw) {
+                    const int ws = __shfl_sync(0xffffffffu, lo, 7 + pw), we = __shfl_sync(0xffffffffu, hi, 7 + pw);
+                    const bool empty = (he <= hs) || (we <= ws);
+                    float best = -FLT_MAX;
+                    // half 0 takes rows hs, hs+2, ...; half 1 rows hs+1, hs+3, ...: same column, opposite bank half
+                    for (int h = hs + half; h < he; h += 2) {
+                        const float* row = lane_base + ((size_t)h * kPitch + ws) * kK;
+                        for (int w = ws; w < we; ++w, row += kK) best = fmaxf(best, *row);
+                    }
+                    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+                    if (half == 0) put(my_stage + c * kBins + ph * 7 + pw, empty ? 0.f : best);
+                }
+            }
+        } else {
+            for (int i = lane; i < kK * kBins; i += 32) put(my_stage + i, 0.f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+            bulk_store_commit(out + (size_t)n * ldo + (size_t)ct * kK * kBins, my_stage, kK * kBins * (unsigned)sizeof(OutT));
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+size_t plane_smem_bytes(int H, size_t esz) {
+    return (size_t)H * kPitch * kK * sizeof(float) + (size_t)kWarps * kK * kBins * esz;
+}
+
+}  // namespace
+
+// Used by i2v_roi_pool_rows (roi_pool.cu) when the shape allows it; returns I2V_ERR_UNSUPPORTED otherwise.
+int roi_pool_rows_plane(const float* features, const float* rois, void* out, int batch, int channels, int height,
+                        int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
+                        int out_dtype, cudaStream_t stream) {
+    const size_t esz = out_dtype == I2V_DT_BF16 ? 2 : 4;
+    const bool ok = pooled_h == 7 && pooled_w == 7 && channels % kK == 0 && width <= kPitch - 1 && batch >= 1 &&
+                    plane_smem_bytes(height, esz) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0 &&
+                    ((size_t)ldo * esz) % 16 == 0;
+    if (!ok) return I2V_ERR_UNSUPPORTED;
+    const int ctiles = channels / kK;
+    int split = 1;
+    while (batch * ctiles * split < 2 * kNumSMs && split * kWarps < num_rois && split < 16) split *= 2;
+    const size_t smem = plane_smem_bytes(height, esz);
+    dim3 grid((unsigned)(batch * ctiles * split));
+    if (out_dtype == I2V_DT_BF16) {
+        auto kern = roi_pool_plane_kernel<__nv_bfloat16>;
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, stream>>>(features, rois, static_cast<__nv_bfloat16*>(out), batch, channels, height,
+                                               width, num_rois, spatial_scale, ldo, split);
+    } else {
+        auto kern = roi_pool_plane_kernel<float>;
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, stream>>>(features, rois, static_cast<float*>(out), batch, channels, height, width,
+                                               num_rois, spatial_scale, ldo, split);
+    }
+    return check_launch("roi_pool_plane_kernel");
+}
+
+}  // namespace i2v

@@ -40,6 +40,51 @@ __global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in,
     }
 }
 
+// Same mapping, eight output columns (one 16-byte store) per thread; `ldo` must be a multiple of 8.  When the input is
+// NHWC bf16 with C % 8 == 0 the eight columns are eight consecutive channels of one tap: one 16-byte load.
+template <typename InT>
+__global__ void __launch_bounds__(256) im2col8_kernel(const InT* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                      int64_t total8, int C, int H, int W, int64_t sn, int64_t sc,
+                                                      int64_t sy, int64_t sx, int KH, int KW, int stride, int pad, int OH,
+                                                      int OW, int64_t ldo, int vec_in) {
+    const int K = KH * KW * C;
+    const int chunks = (int)(ldo >> 3);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total8;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int col0 = (int)(idx % chunks) * 8;
+        const int64_t row = idx / chunks;
+        const int ox = (int)(row % OW);
+        const int oy = (int)((row / OW) % OH);
+        const int64_t n = row / ((int64_t)OW * OH);
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (vec_in) {
+            if (col0 < K) {
+                const int c = col0 % C, tap = col0 / C;
+                const int kx = tap % KW, ky = tap / KW;
+                const int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
+                if (y >= 0 && y < H && x >= 0 && x < W)
+                    pk = *reinterpret_cast<const uint4*>(in + n * sn + c * sc + y * sy + x * sx);
+            }
+        } else {
+            __nv_bfloat16 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = col0 + j;
+                float f = 0.f;
+                if (col < K) {
+                    const int c = col % C, tap = col / C;
+                    const int kx = tap % KW, ky = tap / KW;
+                    const int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
+                    if (y >= 0 && y < H && x >= 0 && x < W) f = to_float(in[n * sn + c * sc + y * sy + x * sx]);
+                }
+                v[j] = __float2bfloat16_rn(f);
+            }
+            pk = *reinterpret_cast<uint4*>(v);
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + col0) = pk;
+    }
+}
+
 __global__ void __launch_bounds__(256) pair_rows_kernel(const float* __restrict__ obj, const int64_t* __restrict__ ixs,
                                                         const int64_t* __restrict__ ixo, __nv_bfloat16* __restrict__ out,
                                                         int64_t total, int num_obj, int E, int64_t ldo) {
@@ -72,6 +117,23 @@ extern "C" int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels
     int64_t total = (int64_t)n * OH * OW * ldo;
     if (total == 0) return I2V_OK;
     I2V_REQUIRE(in && out, "im2col: null pointer");
+    if (ldo % 8 == 0 && ((uintptr_t)out & 15) == 0) {   // 16-byte stores
+        int64_t total8 = total / 8;
+        int grid8 = grid_for(total8, 256, 16);
+        if (in_dtype == I2V_DT_F32) {
+            im2col8_kernel<float><<<grid8, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out),
+                                                             total8, channels, height, width, stride_n, stride_c, stride_y,
+                                                             stride_x, kernel_h, kernel_w, stride, pad, OH, OW, ldo, 0);
+        } else {
+            int vec_in = stride_c == 1 && channels % 8 == 0 && stride_n % 8 == 0 && stride_y % 8 == 0 && stride_x % 8 == 0 &&
+                         ((uintptr_t)in & 15) == 0;
+            im2col8_kernel<__nv_bfloat16><<<grid8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                     static_cast<__nv_bfloat16*>(out), total8, channels,
+                                                                     height, width, stride_n, stride_c, stride_y, stride_x,
+                                                                     kernel_h, kernel_w, stride, pad, OH, OW, ldo, vec_in);
+        }
+        return check_launch("im2col8_kernel");
+    }
     int grid = grid_for(total, 256, 16);
     if (in_dtype == I2V_DT_F32)
         im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out),

@@ -114,14 +114,39 @@ def test_rel_scores_match_torch(ops, p, r, e):
     assert float((got_raw.double() - sim).abs().max()) <= 1e-6
 
 
-def test_roi_pool_rows_equal_the_roi_pool_op(ops):
+@pytest.mark.parametrize("channels,batch", [(64, 1), (24, 1), (32, 3)])   # plane kernel, gather fallback, several frames
+def test_roi_pool_rows_equal_the_roi_pool_op(ops, channels, batch):
     from i2vsgg_b200 import synth
     from i2vsgg_b200._lib import ARGMAX_PLANE
-    feat = torch.from_numpy(synth.feature_map(3, 1, 64)).cuda()
-    rois = torch.from_numpy(synth.rois(4, 50, 1)).cuda()
+    feat = torch.from_numpy(synth.feature_map(3, batch, channels)).cuda()
+    r = synth.rois(4, 50, batch)
+    if batch > 1:
+        r[7, 0], r[19, 0] = -1, batch + 2            # stray frame indices: zero rows
+    rois = torch.from_numpy(r).cuda()
     want, _ = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16, ARGMAX_PLANE)
     rows32 = ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16, dtype=torch.float32)
     assert torch.equal(rows32, want.reshape(50, -1))
-    big = torch.zeros((60, 64 * 49), device="cuda", dtype=torch.bfloat16)
+    big = torch.zeros((60, channels * 49), device="cuda", dtype=torch.bfloat16)
     ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16, out=big[10:60])
     assert torch.equal(big[10:60], want.reshape(50, -1).bfloat16()) and torch.all(big[:10] == 0)
+
+
+@pytest.mark.parametrize("layout,c,h,k,stride,pad,dtype", [("nchw", 2, 32, 5, 2, 2, torch.float32),
+                                                            ("nhwc", 96, 16, 5, 2, 2, torch.bfloat16),
+                                                            ("nhwc", 12, 9, 3, 1, 0, torch.bfloat16),
+                                                            ("nhwc", 128, 8, 8, 1, 0, torch.bfloat16)])
+def test_im2col_matches_unfold(ops, layout, c, h, k, stride, pad, dtype):
+    g = torch.Generator(device="cuda").manual_seed(c + h)
+    n = 5
+    x = torch.randn((n, c, h, h), device="cuda", generator=g).to(dtype)
+    xin = x if layout == "nchw" else x.permute(0, 2, 3, 1).contiguous()
+    kk = k * k * c
+    ld = (kk + 7) // 8 * 8
+    got, (n2, oh, ow) = ops.im2col_bf16(xin, k, stride, pad, layout, ld=ld)
+    # torch's unfold orders a patch (c, ky, kx); ours is (ky, kx, c)
+    want = torch.nn.functional.unfold(x.float(), k, padding=pad, stride=stride)          # [n, c*k*k, oh*ow]
+    want = want.view(n, c, k, k, oh * ow).permute(0, 4, 2, 3, 1).reshape(n * oh * ow, kk).bfloat16()
+    assert (n2, got.shape[0]) == (n, n * oh * ow)
+    assert torch.equal(got[:, :kk], want) and torch.all(got[:, kk:] == 0)
+    got1, _ = ops.im2col_bf16(xin, k, stride, pad, layout, ld=kk + 1 if (kk + 1) % 8 else kk + 3)   # scalar-store path
+    assert torch.equal(got1[:, :kk], want)
