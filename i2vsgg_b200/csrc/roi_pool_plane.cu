@@ -37,6 +37,32 @@ __device__ __forceinline__ void bulk_store_commit(void* gdst, const void* ssrc, 
 __device__ __forceinline__ void put(float* p, float v) { *p = v; }
 __device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// One sweep over the columns [x, x_end) of a bin row that is NR rows tall (NR <= 8).  Half-warp 0 owns rows 0, 2, ...,
+// half-warp 1 rows 1, 3, ... of the bin row: NR/2 loads at compile-time offsets for both halves, plus -- for odd NR -- one
+// more at `tail` (the extra row of half 0; half 1 re-reads its last row, which cannot change a maximum).  No lane-dependent
+// control flow.  Bins tile the columns with at most one shared column, whose value is carried into the next bin.
+template <int NR, typename OutT>
+__device__ __forceinline__ void sweep_bin_row(const float* p, int tail, int x, int lo, int hi, int half, OutT* dst) {
+    constexpr int kRow2 = 2 * kPitch * kK;
+    float v = -FLT_MAX, carry = -FLT_MAX;
+#pragma unroll 1
+    for (int pw = 0; pw < 7; ++pw) {
+        const int we = __shfl_sync(0xffffffffu, hi, 7 + pw);
+        const int ws_next = __shfl_sync(0xffffffffu, lo, 7 + min(pw + 1, 6));
+        float best = carry;
+#pragma unroll 2
+        for (; x < we; ++x, p += kK) {          // the tight part: loads and maxima only
+            v = (NR & 1) ? p[tail] : -FLT_MAX;
+#pragma unroll
+            for (int k = 0; k < NR / 2; ++k) v = fmaxf(v, p[k * kRow2]);
+            best = fmaxf(best, v);
+        }
+        const float r = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+        if (half == 0) put(dst + pw, r);
+        carry = (pw < 6 && ws_next == we - 1) ? v : -FLT_MAX;   // `v` is the bin's last column
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
     roi_pool_plane_kernel(const float* __restrict__ feat, const float* __restrict__ rois, OutT* __restrict__ out,
@@ -94,21 +120,52 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         if (mine) {
+            // regular RoI: every bin column is non-empty.  Consecutive bins then tile [ws[0], we[6]) with at most one
+            // shared column (floor / ceil of the same product), which is what the sweep below relies on.
+            const int next_lo = __shfl_down_sync(0xffffffffu, lo, 1);
+            const unsigned nonempty = __ballot_sync(0xffffffffu, hi > lo);
+            const unsigned tiles = __ballot_sync(0xffffffffu, next_lo >= hi - 1 && next_lo <= hi);
+            const bool regular = ((nonempty >> 7) & 0x7fu) == 0x7fu && ((tiles >> 7) & 0x3fu) == 0x3fu;
 #pragma unroll 1
             for (int ph = 0; ph < 7; ++ph) {
                 const int hs = __shfl_sync(0xffffffffu, lo, ph), he = __shfl_sync(0xffffffffu, hi, ph);
-#pragma unroll 1
-                for (int pw = 0; pw < 7; ++pw) {
-                    const int ws = __shfl_sync(0xffffffffu, lo, 7 + pw), we = __shfl_sync(0xffffffffu, hi, 7 + pw);
-                    const bool empty = (he <= hs) || (we <= ws);
-                    float best = -FLT_MAX;
-                    // half 0 takes rows hs, hs+2, ...; half 1 rows hs+1, hs+3, ...: same column, opposite bank half
-                    for (int h = hs + half; h < he; h += 2) {
-                        const float* row = lane_base + ((size_t)h * kPitch + ws) * kK;
-                        for (int w = ws; w < we; ++w, row += kK) best = fmaxf(best, *row);
+                OutT* dst = my_stage + c * kBins + ph * 7;
+                if (he <= hs) {                       // empty bin row: zeros (roi_pooling_kernel.cu:68-70)
+                    if (half == 0)
+                        for (int pw = 0; pw < 7; ++pw) put(dst + pw, 0.f);
+                    continue;
+                }
+                // half 0 takes rows hs, hs+2, ...; half 1 rows hs+1, hs+3, ...: same column, opposite bank half.
+                // A bin is at most 8 rows tall (H <= 49, checked on the host).
+                const int nr = he - hs;
+                const int myrows = (nr - half + 1) >> 1;
+                constexpr int kRow2 = 2 * kPitch * kK;          // two rows further down, in floats
+                // a one-row bin leaves half 1 without a row of its own: it re-reads half 0's
+                const float* rowp = lane_base + (size_t)(hs + (nr > 1 ? half : 0)) * kPitch * kK;
+                if (regular) {
+                    const int x0 = __shfl_sync(0xffffffffu, lo, 7);
+                    const float* p = rowp + (size_t)x0 * kK;
+                    const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;
+                    switch (nr) {   // uniform
+                        case 1: sweep_bin_row<1>(p, tail, x0, lo, hi, half, dst); break;
+                        case 2: sweep_bin_row<2>(p, tail, x0, lo, hi, half, dst); break;
+                        case 3: sweep_bin_row<3>(p, tail, x0, lo, hi, half, dst); break;
+                        case 4: sweep_bin_row<4>(p, tail, x0, lo, hi, half, dst); break;
+                        case 5: sweep_bin_row<5>(p, tail, x0, lo, hi, half, dst); break;
+                        case 6: sweep_bin_row<6>(p, tail, x0, lo, hi, half, dst); break;
+                        case 7: sweep_bin_row<7>(p, tail, x0, lo, hi, half, dst); break;
+                        default: sweep_bin_row<8>(p, tail, x0, lo, hi, half, dst); break;
                     }
-                    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
-                    if (half == 0) put(my_stage + c * kBins + ph * 7 + pw, empty ? 0.f : best);
+                } else {
+#pragma unroll 1
+                    for (int pw = 0; pw < 7; ++pw) {
+                        const int ws = __shfl_sync(0xffffffffu, lo, 7 + pw), we = __shfl_sync(0xffffffffu, hi, 7 + pw);
+                        float best = -FLT_MAX;
+                        for (int h = 0; h < myrows; ++h)
+                            for (int w = ws; w < we; ++w) best = fmaxf(best, rowp[(size_t)h * kRow2 + (size_t)w * kK]);
+                        best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
+                        if (half == 0) put(dst + pw, we <= ws ? 0.f : best);
+                    }
                 }
             }
         } else {
@@ -133,7 +190,8 @@ int roi_pool_rows_plane(const float* features, const float* rois, void* out, int
                         int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
                         int out_dtype, cudaStream_t stream) {
     const size_t esz = out_dtype == I2V_DT_BF16 ? 2 : 4;
-    const bool ok = pooled_h == 7 && pooled_w == 7 && channels % kK == 0 && width <= kPitch - 1 && batch >= 1 &&
+    const bool ok = pooled_h == 7 && pooled_w == 7 && channels % kK == 0 && width <= kPitch - 1 && height <= 49 &&
+                    batch >= 1 &&
                     plane_smem_bytes(height, esz) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0 &&
                     ((size_t)ldo * esz) % 16 == 0;
     if (!ok) return I2V_ERR_UNSUPPORTED;

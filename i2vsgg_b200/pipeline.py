@@ -66,25 +66,30 @@ class HostPipeline:
         self._host = None
 
     # ------------------------------------------------------------------ device-resident inputs
-    def device_step(self, cls_prob, bbox_pred, im_info, features, grad_out, timer: StageTimer | None = None):
+    def _run(self, cls_prob, bbox_pred, im_info, features, grad_out, rois, pooled, grad_in, frames, timer=None):
+        """proposal layer -> RoIAlignAvg forward -> backward for `frames` frames (all arguments are that many frames)."""
         lib, s = self.lib, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n = frames * self.post
         marks = [timer.mark()] if timer else None
-        check(lib.i2v_proposal_forward(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(self.anchors), self.B, self.A,
-                                       self.H, self.W, self.stride, self.pre, self.post, self.thr, _p(self.rois),
+        check(lib.i2v_proposal_forward(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(self.anchors), frames, self.A,
+                                       self.H, self.W, self.stride, self.pre, self.post, self.thr, _p(rois),
                                        _p(self.counts), _p(self.ws_prop), self.ws_prop.numel(), s), "proposal_forward")
         if timer:
             marks.append(timer.mark())
-        check(lib.i2v_roi_align_forward(_p(features), _p(self.rois), _p(self.pooled), self.B, self.C, self.H, self.W,
-                                        self.N, self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO, _p(self.ws_roi),
+        check(lib.i2v_roi_align_forward(_p(features), _p(rois), _p(pooled), frames, self.C, self.H, self.W,
+                                        n, self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO, _p(self.ws_roi),
                                         self.ws_roi.numel(), s), "roi_align_forward")
         if timer:
             marks.append(timer.mark())
-        check(lib.i2v_roi_align_backward(_p(grad_out), None, _p(self.rois), _p(self.grad_in), self.B, self.C, self.H,
-                                         self.W, self.N, self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO,
+        check(lib.i2v_roi_align_backward(_p(grad_out), None, _p(rois), _p(grad_in), frames, self.C, self.H,
+                                         self.W, n, self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO,
                                          _p(self.ws_roi), self.ws_roi.numel(), s), "roi_align_backward")
         if timer:
             marks.append(timer.mark())
             timer.add(marks)
+
+    def device_step(self, cls_prob, bbox_pred, im_info, features, grad_out, timer: StageTimer | None = None):
+        self._run(cls_prob, bbox_pred, im_info, features, grad_out, self.rois, self.pooled, self.grad_in, self.B, timer)
         return self.rois, self.pooled, self.grad_in
 
     # ------------------------------------------------------------------ pinned host inputs and outputs
@@ -97,25 +102,47 @@ class HostPipeline:
             d["rois_h"] = torch.empty(self.rois.shape, dtype=torch.float32).pin_memory()
             d["pooled_h"] = torch.empty(self.pooled.shape, dtype=torch.float32).pin_memory()
             d["grad_in_h"] = torch.empty(self.grad_in.shape, dtype=torch.float32).pin_memory()
+            d["s_in"], d["s_out"] = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
             self._host = d
             self.h2d_bytes = sum(t.numel() * 4 for t in (cls_prob, bbox_pred, im_info, features, grad_out))
             self.d2h_bytes = sum(d[k].numel() * 4 for k in ("rois_h", "pooled_h", "grad_in_h"))
         return self._host
 
-    def host_step(self, cls_prob, bbox_pred, im_info, features, grad_out):
-        """Host buffers in, host buffers out: copies every input to the device, runs the step, copies every result
-        (proposals, pooled features, feature gradient) back, and returns when they are in host memory."""
+    def host_step(self, cls_prob, bbox_pred, im_info, features, grad_out, chunk_frames: int = 4):
+        """Host buffers in, host buffers out: every input is copied to the device, the step runs, every result
+        (proposals, pooled features, feature gradient) is copied back; returns when they are in host memory.
+
+        Frames are independent, so the batch moves in chunks of `chunk_frames`: chunk k+1 is on its way in (copy
+        engine 1) while chunk k computes and chunk k-1 is on its way out (copy engine 2).  The PCIe link is full duplex,
+        which makes the step cost max(bytes in, bytes out) / link instead of their sum."""
         d = self._host_buffers(cls_prob, bbox_pred, im_info, features, grad_out)
-        d["cls"].copy_(cls_prob, non_blocking=True)
-        d["reg"].copy_(bbox_pred, non_blocking=True)
-        d["info"].copy_(im_info, non_blocking=True)
-        d["feat"].copy_(features, non_blocking=True)
-        d["grad"].copy_(grad_out, non_blocking=True)
-        self.device_step(d["cls"], d["reg"], d["info"], d["feat"], d["grad"])
-        d["rois_h"].copy_(self.rois, non_blocking=True)
-        d["pooled_h"].copy_(self.pooled, non_blocking=True)
-        d["grad_in_h"].copy_(self.grad_in, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main, s_in, s_out = torch.cuda.current_stream(), d["s_in"], d["s_out"]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        post = self.post
+        for f0 in range(0, self.B, chunk_frames):
+            f1 = min(self.B, f0 + chunk_frames)
+            r0, r1 = f0 * post, f1 * post
+            with torch.cuda.stream(s_in):
+                d["cls"][f0:f1].copy_(cls_prob[f0:f1], non_blocking=True)
+                d["reg"][f0:f1].copy_(bbox_pred[f0:f1], non_blocking=True)
+                d["info"][f0:f1].copy_(im_info[f0:f1], non_blocking=True)
+                d["feat"][f0:f1].copy_(features[f0:f1], non_blocking=True)
+                d["grad"][r0:r1].copy_(grad_out[r0:r1], non_blocking=True)
+                ready = s_in.record_event()
+            main.wait_event(ready)
+            self._run(d["cls"][f0:f1], d["reg"][f0:f1], d["info"][f0:f1], d["feat"][f0:f1], d["grad"][r0:r1],
+                      self.rois[f0:f1], self.pooled[r0:r1], self.grad_in[f0:f1], f1 - f0)
+            if f0:
+                self.rois[f0:f1, :, 0] += float(f0)      # frame indices of the whole batch, as device_step writes them
+            done = main.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                d["rois_h"][f0:f1].copy_(self.rois[f0:f1], non_blocking=True)
+                d["pooled_h"][r0:r1].copy_(self.pooled[r0:r1], non_blocking=True)
+                d["grad_in_h"][f0:f1].copy_(self.grad_in[f0:f1], non_blocking=True)
+        main.wait_stream(s_out)
+        main.synchronize()
         return d["rois_h"], d["pooled_h"], d["grad_in_h"]
 
     h2d_bytes = 0

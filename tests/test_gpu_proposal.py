@@ -170,3 +170,23 @@ def test_nms_properties_at_full_size(ops):
     iou = iw * ih / (area[:, None] + area[None, :] - iw * ih)
     iou.fill_diagonal_(0)
     assert float(iou.max()) <= 0.7 + 1e-6
+
+
+def test_host_pipeline_chunked_copy_equals_device_step():
+    """The end-to-end call (pinned host buffers in and out, frames streamed in chunks over both copy engines) returns
+    exactly what the device-resident step computes."""
+    from i2vsgg_b200.pipeline import HostPipeline
+    frames, ch = 6, 32
+    dev = torch.device("cuda", 0)
+    cls, reg = synth.rpn_outputs(77, batch=frames)
+    info = synth.im_info(frames)
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn((frames, ch, 38, 63), generator=g).pin_memory()
+    grad = torch.randn((frames * 50, ch, 7, 7), generator=g).pin_memory()
+    cls, reg, info = (torch.from_numpy(a).pin_memory() for a in (cls, reg, info))
+    pipe = HostPipeline(dev, frames, ch, 38, 63, 7, 1 / 16, 3000, 50, 0.7)
+    want = [t.clone() for t in pipe.device_step(*(t.to(dev) for t in (cls, reg, info, feat, grad)))]
+    for chunk in (4, 1, 6):
+        got = pipe.host_step(cls, reg, info, feat, grad, chunk_frames=chunk)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b.cpu())
