@@ -736,6 +736,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// roi_align_bwd_rows.cu: the row-owner backward
+size_t bwd_rows_smem_bytes(int H, int W);
+bool bwd_rows_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
+int launch_bwd_rows(const float* grad_out, const LatticeRoi* tab, void* rtab_space, const int* order, const int* starts,
+                    float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
+
 struct LatticeWs {
     LatticeRoi* tab;
     PlaneTab* ptab;   // the plane tables share one allocation: the forward view or the backward view of a call
@@ -852,7 +858,7 @@ static int roi_align_check(const char* who, const void* a, const void* b, const 
                            int& GH, int& GW) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0, "%s: negative size", who);
     I2V_REQUIRE(pool_mode >= I2V_POOL_NONE && pool_mode <= I2V_POOL_MAX, "%s: bad pool_mode %d", who, pool_mode);
-    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_PLANE, "%s: bad impl %d", who, impl);
+    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_ROWS, "%s: bad impl %d", who, impl);
     GH = pooled_h + (pool_mode != I2V_POOL_NONE);
     GW = pooled_w + (pool_mode != I2V_POOL_NONE);
     I2V_REQUIRE(pooled_h >= 1 && pooled_w >= 1 && GH >= 2 && GW >= 2 && GH <= kMaxLattice && GW <= kMaxLattice,
@@ -884,7 +890,7 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
                             pooled_h, pooled_w, pool_mode, impl, GH, GW));
     if (num_rois == 0 || channels == 0) return I2V_OK;
     bool can_plane = plane_forward_ok(out, batch, channels, height, width, pooled_h, pooled_w);
-    if (impl == I2V_IMPL_PLANE && !can_plane) {
+    if ((impl == I2V_IMPL_PLANE || impl == I2V_IMPL_ROWS) && !can_plane) {
         set_error("roi_align_forward: the plane kernel needs a 7x7 output, C %% 16 == 0, a 16-byte aligned output and "
                   "16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
@@ -924,10 +930,18 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
     // the plane kernel overwrites grad_in, so it cannot serve the accumulate-into-caller's-buffer launcher
     bool can_plane = zero_first && num_rois > 0 &&
                      plane_backward_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
-    if (impl == I2V_IMPL_PLANE && !can_plane) {
-        set_error("roi_align_backward: the plane kernel needs a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
+    bool can_rows = zero_first && num_rois > 0 &&
+                    bwd_rows_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows)) {
+        set_error("roi_align_backward: the plane kernels need a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
                   "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
+    }
+    if (can_rows && (impl == I2V_IMPL_AUTO || impl == I2V_IMPL_ROWS)) {
+        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        return launch_bwd_rows(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
+                               num_rois, pool_mode, stream);
     }
     if (can_plane && impl != I2V_IMPL_GATHER) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));

@@ -95,10 +95,10 @@ def test_roi_align_empty(ops):
 
 
 @pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane", "auto"])
+@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "auto"])
 @pytest.mark.parametrize("case", CASES)
 def test_roi_align_backward(ops, orc, case, impl, pool):
-    if impl == "plane" and pool == "max":
+    if impl in ("plane", "rows") and pool == "max":
         pytest.skip("the max pool's arg-max routing needs the features: gather kernel only")
     B, C, H, W, N = case
     feat = synth.feature_map(100 + B, B, C, H, W)
@@ -126,10 +126,11 @@ def test_roi_align_backward_small_and_repeated_cells(ops, orc):
     for pool in ("avg", "none"):
         want = orc.roi_align_pooled_backward(g, None if pool != "max" else None, rois, 7, 7, SCALE, pool) \
             if False else orc.roi_align_pooled_backward(g, np.zeros(feat_shape, np.float32), rois, 7, 7, SCALE, pool)
-        got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, "plane")
-        close(got, want)
-        again = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, "plane")
-        assert torch.equal(got, again)      # no atomics: bit-reproducible
+        for impl in ("plane", "rows"):
+            got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
+            close(got, want)
+            again = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
+            assert torch.equal(got, again)      # no atomics: bit-reproducible
 
 
 def test_roi_align_backward_frames_without_rois_are_zeroed(ops, orc):
