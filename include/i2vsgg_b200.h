@@ -76,8 +76,8 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
 #define I2V_IMPL_AUTO 0    /* plane-resident kernel when the shape allows it, else the gather kernel */
 #define I2V_IMPL_GATHER 1  /* one thread per output element, L1/L2 gathers (any shape)                */
 #define I2V_IMPL_PLANE 2   /* frame plane staged in shared memory; I2V_ERR_UNSUPPORTED if it cannot    */
-#define I2V_IMPL_ROWS 3    /* backward only: plane-resident, warps own feature rows (the default when the shape
-                              allows it; forward treats it like I2V_IMPL_PLANE)                                    */
+#define I2V_IMPL_ROWS 3    /* backward only: plane-resident, warps own feature rows (bank-conflict free by
+                              construction; forward treats it like I2V_IMPL_PLANE)                                 */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.
