@@ -98,6 +98,21 @@ __global__ void __launch_bounds__(256) pair_rows_kernel(const float* __restrict_
     }
 }
 
+
+// out[p][:] = src[idx[p]][:] for bf16 rows, 16 bytes per thread (cols % 8 == 0, 16-byte aligned pitches).
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int64_t* __restrict__ idx,
+                                                          __nv_bfloat16* __restrict__ out, int64_t total8, int num_src,
+                                                          int chunks, int64_t lds, int64_t ldo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const int64_t p = i / chunks;
+        const int64_t r = idx[p];
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r >= 0 && r < num_src) v = *reinterpret_cast<const uint4*>(src + r * lds + ch * 8);
+        *reinterpret_cast<uint4*>(out + p * ldo + ch * 8) = v;
+    }
+}
+
 }  // namespace
 }  // namespace i2v
 
@@ -156,4 +171,18 @@ extern "C" int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const in
     pair_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(obj, ixs, ixo, static_cast<__nv_bfloat16*>(out), total,
                                                                num_obj, emb_dim, ldo);
     return check_launch("pair_rows_kernel");
+}
+
+extern "C" int i2v_gather_rows_bf16(const void* src, const int64_t* idx, void* out, int num_src, int num_out, int cols,
+                                    long long lds, long long ldo, cudaStream_t stream) {
+    I2V_REQUIRE(num_src >= 0 && num_out >= 0 && cols >= 0 && lds >= cols && ldo >= cols, "gather_rows: bad shape");
+    if (num_out == 0 || cols == 0) return I2V_OK;
+    I2V_REQUIRE(src && idx && out, "gather_rows: null pointer");
+    I2V_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                "gather_rows: rows must be multiples of 16 bytes with 16-byte aligned pitches");
+    int64_t total8 = (int64_t)num_out * (cols / 8);
+    gather_rows_kernel<<<grid_for(total8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), idx,
+                                                                  static_cast<__nv_bfloat16*>(out), total8, num_src, cols / 8,
+                                                                  lds, ldo);
+    return check_launch("gather_rows_kernel");
 }

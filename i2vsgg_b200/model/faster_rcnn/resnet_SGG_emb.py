@@ -103,7 +103,10 @@ class vrd(nn.Module):
         return self
 
     # ------------------------------------------------------------------ forward
-    def forward(self, fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2, return_numpy: bool = True):
+    def forward(self, fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2, return_numpy: bool = True, rel_unique=None):
+        """`rel_unique=(rep, inverse)` (see `i2vsgg_b200.sgg.unordered_pairs`) tells the head that rel_boxes[inverse[p]]
+        repeats rel_boxes[rep]: the union rows are then pooled and pushed through fc6 / fc7 / fc8 once per distinct box and
+        fanned out afterwards -- bit-identical to the full computation, half the work for ordered pairs."""
         if self.training:
             raise NotImplementedError("i2vsgg_b200 vrd implements the inference path; call .eval() first "
                                       "(training mode applies dropout, resnet_SGG_emb.py:148-149)")
@@ -119,18 +122,28 @@ class vrd(nn.Module):
         ix2 = _dev(ix2, dev, torch.int64).reshape(-1)
         n_obj, n_pair = boxes.size(0), rel_boxes.size(0)
         ps = self.pool_size
+        if rel_unique is not None:
+            rep, inverse = rel_unique
+            pool_boxes = rel_boxes.index_select(0, rep.to(dev))
+            inverse = inverse.to(dev)
+        else:
+            pool_boxes, inverse = rel_boxes, None
+        n_uni = pool_boxes.size(0)
 
         # roi_pool of objects and unions -> one bf16 matrix; fc6 / fc7 over all rows at once (:144-149, :158-163)
         k6 = self.in_channels * ps * ps
-        pooled = torch.empty((n_obj + n_pair, k6), dtype=torch.bfloat16, device=dev)
+        pooled = torch.empty((n_obj + n_uni, k6), dtype=torch.bfloat16, device=dev)
         ops.roi_pool_rows(fmap, boxes, ps, ps, self.spatial_scale, out=pooled[:n_obj])
-        ops.roi_pool_rows(fmap, rel_boxes, ps, ps, self.spatial_scale, out=pooled[n_obj:])
+        ops.roi_pool_rows(fmap, pool_boxes, ps, ps, self.spatial_scale, out=pooled[n_obj:])
         h = self.fc7(self.fc6(pooled))
         obj_feature = self.so_vis_embeddings(h[:n_obj], out_dtype=torch.float32)            # :150
 
         fusion = torch.empty((n_pair, self.n_fusion), dtype=torch.bfloat16, device=dev)
         col = 0
-        self.fc8(h[n_obj:], out=fusion[:, col:col + 256])                                   # :164
+        if inverse is None:
+            self.fc8(h[n_obj:], out=fusion[:, col:col + 256])                               # :164
+        else:
+            ops.gather_rows_bf16(self.fc8(h[n_obj:]), inverse, out=fusion[:, col:col + 256])
         col += 256
         if self.args.use_obj_visual:                                                        # :166-170
             self.fc_so(ops.pair_rows_bf16(obj_feature, ix1, ix2), out=fusion[:, col:col + 256])

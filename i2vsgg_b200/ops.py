@@ -357,3 +357,19 @@ def pair_rows_bf16(obj, ixs, ixo, out=None):
         check(load().i2v_pair_rows_bf16(_p(obj), _p(ixs), _p(ixo), _p(out), N, P, E, out.stride(0), _stream()),
               "i2v_pair_rows_bf16")
     return out
+
+
+def gather_rows_bf16(src, idx, out=None):
+    """out[p] = src[idx[p]] for bf16 rows; `out` may be a column slice of a wider matrix."""
+    if not src.is_cuda or src.dtype != torch.bfloat16 or src.dim() != 2 or src.stride(1) != 1:
+        raise _lib.I2VError("gather_rows_bf16: expected a 2-d bf16 CUDA tensor with contiguous rows")
+    idx = idx.long().contiguous()
+    P, D = idx.numel(), src.size(1)
+    if out is None:
+        out = torch.empty((P, D), dtype=torch.bfloat16, device=src.device)
+    if out.shape != (P, D) or out.stride(1) != 1 or out.dtype != torch.bfloat16:
+        raise _lib.I2VError("gather_rows_bf16: bad `out`")
+    with torch.cuda.device(src.device):
+        check(load().i2v_gather_rows_bf16(_p(src), _p(idx), _p(out), src.size(0), P, D, src.stride(0), out.stride(0),
+                                          _stream()), "i2v_gather_rows_bf16")
+    return out

@@ -26,6 +26,27 @@ def build_pairs(pred_boxes, im_h: float, im_w: float, device="cuda", margin: flo
     return ops.pair_build(boxes, float(im_h), float(im_w), float(margin), want_masks)
 
 
+_UNIQUE_CACHE = {}
+
+
+def unordered_pairs(num_boxes: int, device="cuda"):
+    """For the ordered pair list of `build_pairs` (p = i*(N-1) + j - (j > i)): the positions `rep` [U] of the pairs with
+    i < j (one representative per unordered pair, U = N(N-1)/2) and `inverse` [P] mapping every ordered pair to its
+    representative.  The union boxes of (i,j) and (j,i) are the same box, so everything `vrd` computes from rel_boxes
+    alone (RoIPool, fc6, fc7, fc8) needs to run on `rel_boxes[rep]` only.  Pure index arithmetic, cached per N."""
+    key = (int(num_boxes), str(device))
+    if key not in _UNIQUE_CACHE:
+        n = int(num_boxes)
+        i, j = torch.triu_indices(n, n, 1)
+        rep = i * (n - 1) + j - 1
+        u = torch.arange(rep.numel())
+        inverse = torch.empty((n * (n - 1),), dtype=torch.int64)
+        inverse[rep] = u
+        inverse[j * (n - 1) + i] = u              # the pair (j, i), j > i, sits at j*(N-1) + i
+        _UNIQUE_CACHE[key] = (rep.to(device), inverse.to(device))
+    return _UNIQUE_CACHE[key]
+
+
 def frame_triplets(rel_score, confs, classes, boxes, ixs, ixo, top_k: int = 100):
     """-> (records [top_k,13] fp32, count int32[1]); record = (conf, cls_s, rel, cls_o, sub box, obj box, pair idx)."""
     dev = rel_score.device

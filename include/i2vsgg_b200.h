@@ -188,6 +188,11 @@ int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int heigh
  * [P, 2E] with pitch ldo; obj [N,E] fp32, ixs/ixo [P] int64. */
 int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,
                        int num_pairs, int emb_dim, long long ldo, cudaStream_t stream);
+/* out[p] = src[idx[p]] for bf16 rows (cols % 8 == 0; pitches in elements, multiples of 8).  Used to fan the rows computed
+ * once per UNORDERED pair back out to both orderings: the union boxes of (i,j) and (j,i) are the same box
+ * (resnet_SGG_emb.py:240-244 is symmetric), so their pooled / fc6 / fc7 / fc8 rows are identical. */
+int i2v_gather_rows_bf16(const void* src, const int64_t* idx, void* out, int num_src, int num_out, int cols,
+                         long long lds, long long ldo, cudaStream_t stream);
 /* resnet_SGG_emb.py:207-219: scores[P,R] = softmax_R(normalize(x[P,E]) . normalize(prd[R,E])^T); the softmax is
  * the eval-mode branch (apply_softmax != 0).  fp32 throughout. */
 size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim);

@@ -152,6 +152,22 @@ def test_vrd_config3_spot_rows(orc):
     np.testing.assert_allclose(got_s, want_s, rtol=2e-2, atol=1e-6)
 
 
+def test_vrd_unordered_pair_shortcut_is_bit_identical(orc):
+    """(i,j) and (j,i) share their union box: pooling / fc6 / fc7 / fc8 once per unordered pair changes no bit."""
+    from i2vsgg_b200 import sgg
+    args = synth.VrdArgs(vrd_in_channels=64, vrd_hidden=512)
+    params = synth.vrd_params(99, args)
+    prd = synth.prd_vectors(5, args.num_relations)
+    fmap = synth.feature_map(31, 1, 64)
+    boxes, rel, masks, classes, ixs, ixo = frame_inputs(orc, 33, 11)
+    net = build(args, params, prd)
+    s0, f0 = net(fmap, boxes, rel, masks, classes, ixs, ixo, return_numpy=False)
+    rep, inverse = sgg.unordered_pairs(11)
+    assert torch.equal(torch.from_numpy(rel).cuda()[rep][inverse], torch.from_numpy(rel).cuda())
+    s1, f1 = net(fmap, boxes, rel, masks, classes, ixs, ixo, return_numpy=False, rel_unique=(rep, inverse))
+    assert torch.equal(s0, s1) and torch.equal(f0, f1)
+
+
 def test_vrd_refuses_training_mode_and_cpu():
     from i2vsgg_b200.model.faster_rcnn.resnet_SGG_emb import vrd
     args = synth.VrdArgs(vrd_in_channels=16, vrd_hidden=64)
