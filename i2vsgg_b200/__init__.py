@@ -5,7 +5,8 @@
                        ``model.nms``, ``model.rpn.proposal_layer``, ``model.roi_layers``) with the same call
                        signatures; ``install_as_model()`` makes it importable under the reference's own
                        dotted names so it drops in over the PyTorch-0.4 cffi extensions.
-``i2vsgg_b200.sgg``    pair-feature builder / triplet selection of the SGG stage
+``i2vsgg_b200.sgg``    pair-feature builder / triplet selection of the SGG stage; the relation head itself is
+                       ``i2vsgg_b200.model.faster_rcnn.resnet_SGG_emb.vrd`` (``install_vrd()`` patches it into the reference)
 ``i2vsgg_b200.shard``  frame sharding over ranks and the triplet all-gather
 """
 from __future__ import annotations
@@ -36,3 +37,15 @@ def install_as_model(force: bool = False) -> None:
         if name in sys.modules and not force:
             continue
         sys.modules[name] = importlib.import_module("i2vsgg_b200." + name)
+
+
+def install_vrd(reference_module=None):
+    """Replaces the class ``vrd`` of the reference's ``model.faster_rcnn.resnet_SGG_emb`` (lib/model/faster_rcnn/
+    resnet_SGG_emb.py:64) by the sm_100a relation head.  Only the class is patched: the module also holds the ResNet
+    backbone, which is not part of this path.  Returns the class."""
+    from .model.faster_rcnn.resnet_SGG_emb import vrd
+    if reference_module is None:
+        reference_module = sys.modules.get("model.faster_rcnn.resnet_SGG_emb")
+    if reference_module is not None:
+        reference_module.vrd = vrd
+    return vrd
