@@ -43,6 +43,12 @@ def algorithmic_bytes(frames: int, rois: int):
     return {"roi_align_fwd": feat + rois * 20 + pooled, "roi_align_bwd": pooled + feat + rois * 20}
 
 
+def measured_traffic():
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), or {}."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -232,7 +238,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "stages_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": measured_traffic().get(top), "peak_source": which,
                          "algorithmic_bytes": alg[top],
                          "other": {k: {"achieved": alg[k] / (stage_ms[k] * 1e-3) / 1e9,
                                        "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / peak} for k in alg}},
