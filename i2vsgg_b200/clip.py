@@ -1,0 +1,67 @@
+"""A clip through the SGG stage, sharded over ranks (BASELINE.json configs[4]).
+
+Each rank takes a contiguous chunk of the clip's frames (`shard.frame_range`) and runs, a few frames per launch group:
+pair enumeration + union boxes + dual masks (`sgg.build_pairs`), the relation head (`vrd.forward` with the
+unordered-pair shortcut) and the per-frame top-100 triplet selection (`ops.triplet_topk`); the only exchange is the
+all-gather of the [frames, 100, 13] records into video order (`shard.all_gather_triplets`), after which the temporal
+association of lib/utils.py:461-526 can run on any rank.  Mirrors the per-frame loop of test_net_SGG_emb.py:150-215.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops, sgg, shard
+
+
+class ClipRunner:
+    def __init__(self, head, im_h: float, im_w: float, frames_per_group: int = 4, top_k: int = shard.TOP_K):
+        self.head, self.im_h, self.im_w = head, float(im_h), float(im_w)
+        self.group, self.top_k = int(frames_per_group), int(top_k)
+
+    def _group(self, fmap, boxes, classes, conf):
+        """fmap [F,C,H,W], boxes [F,N,4], classes [F,N], conf [F,N] (device) -> records [F,top_k,13], counts [F]."""
+        F, N = boxes.shape[:2]
+        dev = fmap.device
+        P = N * (N - 1)
+        rep1, inv1 = sgg.unordered_pairs(N, dev)
+        U = rep1.numel()
+        ixs_l, ixo_l, rel_l, mask_l = [], [], [], []
+        for f in range(F):
+            ixs, ixo, rel, masks = sgg.build_pairs(boxes[f], self.im_h, self.im_w, device=dev)
+            rel[:, 0] = float(f)                                     # RoI rows carry the frame index of the group
+            ixs_l.append(ixs + f * N)
+            ixo_l.append(ixo + f * N)
+            rel_l.append(rel)
+            mask_l.append(masks)
+        rois = torch.cat([torch.arange(F, device=dev, dtype=torch.float32).repeat_interleave(N)[:, None],
+                          boxes.reshape(F * N, 4)], 1)
+        offs = torch.arange(F, device=dev)
+        rep = (rep1[None, :] + offs[:, None] * P).reshape(-1)
+        inv = (inv1[None, :] + offs[:, None] * U).reshape(-1)
+        ixs, ixo = torch.cat(ixs_l), torch.cat(ixo_l)
+        scores, _ = self.head(fmap, rois, torch.cat(rel_l), torch.cat(mask_l), None, ixs, ixo, return_numpy=False,
+                              rel_unique=(rep, inv))
+        rec = torch.empty((F, self.top_k, shard.RECORD_WIDTH), dtype=torch.float32, device=dev)
+        cnt = torch.empty((F,), dtype=torch.int32, device=dev)
+        for f in range(F):
+            r, c = ops.triplet_topk(scores[f * P:(f + 1) * P], conf[f], classes[f], boxes[f], ixs_l[f] - f * N,
+                                    ixo_l[f] - f * N, self.top_k)
+            rec[f], cnt[f] = r, c[0]
+        return rec, cnt
+
+    def run(self, fmaps, boxes, classes, conf, num_frames: int, rank: int = 0, world: int = 1, group=None):
+        """This rank's frames (`fmaps` [f,C,H,W], `boxes` [f,N,4], `classes` [f,N], `conf` [f,N], in clip order)
+        -> (records [num_frames, top_k, 13], counts [num_frames]) of the WHOLE clip on every rank."""
+        lo, hi = shard.frame_range(num_frames, rank, world)
+        assert fmaps.shape[0] == hi - lo, "pass exactly the frames of shard.frame_range(num_frames, rank, world)"
+        recs, cnts = [], []
+        for f0 in range(0, hi - lo, self.group):
+            f1 = min(hi - lo, f0 + self.group)
+            r, c = self._group(fmaps[f0:f1], boxes[f0:f1], classes[f0:f1], conf[f0:f1])
+            recs.append(r)
+            cnts.append(c)
+        dev = fmaps.device
+        rec = torch.cat(recs) if recs else torch.empty((0, self.top_k, shard.RECORD_WIDTH), device=dev)
+        cnt = torch.cat(cnts) if cnts else torch.empty((0,), dtype=torch.int32, device=dev)
+        return shard.all_gather_triplets(rec, cnt, num_frames, group)

@@ -177,3 +177,27 @@ def test_vrd_refuses_training_mode_and_cpu():
     with pytest.raises(RuntimeError):
         net.eval()(np.zeros((1, 16, 38, 63), np.float32), np.zeros((2, 5)), np.zeros((2, 5)), np.zeros((2, 2, 32, 32)),
                    [1, 1], [0, 1], [1, 0])
+
+
+def test_clip_runner_groups_frames_without_changing_records(orc):
+    """ClipRunner batches frames through one `vrd.forward`; the per-frame records must not depend on the grouping, and
+    must be what `sgg.detection_output`'s kernel selects from the per-frame scores."""
+    from i2vsgg_b200 import ops, sgg, shard
+    from i2vsgg_b200.clip import ClipRunner
+    args = synth.VrdArgs(vrd_in_channels=32, vrd_hidden=256)
+    head = build(args, synth.vrd_params(3, args), synth.prd_vectors(5, args.num_relations))
+    frames, n = 5, 9
+    boxes, classes, conf = synth.clip_detections(8, frames, n)
+    fmaps = torch.from_numpy(synth.feature_map(50, frames, 32)).cuda()
+    b = torch.from_numpy(boxes).cuda()
+    c = torch.from_numpy(np.tile(classes, (frames, 1))).cuda()
+    s = torch.from_numpy(np.tile(conf, (frames, 1))).cuda()
+    rec1, cnt1 = ClipRunner(head, synth.IM_H, synth.IM_W, 1).run(fmaps, b, c, s, frames)
+    rec3, cnt3 = ClipRunner(head, synth.IM_H, synth.IM_W, 3).run(fmaps, b, c, s, frames)
+    assert torch.equal(rec1, rec3) and torch.equal(cnt1, cnt3) and rec1.shape == (frames, shard.TOP_K, shard.RECORD_WIDTH)
+    # frame 2 by hand: pair build -> head -> top-k
+    ixs, ixo, rel, masks = sgg.build_pairs(b[2], synth.IM_H, synth.IM_W)
+    rois = torch.cat([torch.zeros((n, 1), device="cuda"), b[2]], 1)
+    scores, _ = head(fmaps[2:3], rois, rel, masks, None, ixs, ixo, return_numpy=False)
+    want, wc = ops.triplet_topk(scores, s[2], c[2], b[2], ixs, ixo, shard.TOP_K)
+    assert torch.equal(rec1[2], want) and int(cnt1[2]) == int(wc[0])
