@@ -373,3 +373,27 @@ def gather_rows_bf16(src, idx, out=None):
         check(load().i2v_gather_rows_bf16(_p(src), _p(idx), _p(out), src.size(0), P, D, src.stride(0), out.stride(0),
                                           _stream()), "i2v_gather_rows_bf16")
     return out
+
+
+def greedy_association(records, counts, frame_numbers=None, source_frame=None, max_traj: int = 100):
+    """lib/utils.py:134-182 on the device.  records [F,K,13] fp32, counts [F] int32 ->
+    (rel_id [F,K] int32, order [F,K] int32, rel_info [F*K,6] int32, rel_score [F*K] float64, num_rel int32[1])."""
+    records = _f32(records, "records")
+    F, K, w = records.shape
+    if w != 13:
+        raise _lib.I2VError("greedy_association: records must be [F, K, 13]")
+    dev = records.device
+    i32 = lambda t: None if t is None else torch.as_tensor(t, device=dev).to(torch.int32).contiguous()
+    counts, frame_numbers, source_frame = i32(counts), i32(frame_numbers), i32(source_frame)
+    rel_id = torch.empty((F, K), dtype=torch.int32, device=dev)
+    order = torch.empty((F, K), dtype=torch.int32, device=dev)
+    info = torch.zeros((max(F * K, 1), 6), dtype=torch.int32, device=dev)
+    score = torch.zeros((max(F * K, 1),), dtype=torch.float64, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.i2v_association_workspace_bytes(F, K), dev)
+        check(lib.i2v_greedy_association(_p(records), _p(counts), _p(frame_numbers), _p(source_frame), F, K, int(max_traj),
+                                         _p(rel_id), _p(order), _p(info), _p(score), _p(num), _p(ws), ws.numel(),
+                                         _stream()), "i2v_greedy_association")
+    return rel_id, order, info, score, num

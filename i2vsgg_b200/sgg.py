@@ -2,6 +2,7 @@
 
 ``build_pairs``       faster_rcnn_SGG_emb.py:597-606 (ordered pairs) + :649-656 (union boxes, dual masks) in one launch
 ``detection_output``  lib/utils.py:584-627 (top-100 triplets of a frame) on the device
+``association``       lib/utils.py:461-526 + :134-182 (per-frame triplets -> video relations), greedy matching on the device
 """
 from __future__ import annotations
 
@@ -75,3 +76,80 @@ def detection_output(vrd_data):
     sub_bboxes_im[:k] = rec[:k, 4:8]
     obj_bboxes_im[:k] = rec[:k, 8:12]
     return rlp_labels_im, rec[:k, 0].copy(), sub_bboxes_im, obj_bboxes_im, rec[:k, 12].astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------ temporal association
+def _fill_empty_frames(counts, invalid_num: int = 4):
+    """lib/utils.py:470-518, index arithmetic only: which frame position a frame without predictions borrows them from
+    (nearest non-empty neighbour, the earlier one on ties), unless every frame within +-4 positions is empty too."""
+    n = len(counts)
+    empty = [c == 0 for c in counts]
+    src = list(range(n))
+    tmp = [-1] * n
+    for i in range(n):
+        if empty[i]:
+            j = i - 1
+            while j >= 0 and empty[j]:
+                j -= 1
+            left = 0 if j < 0 else i - j
+            j = i + 1
+            while j < n and empty[j]:
+                j += 1
+            right = 0 if j >= n else j - i
+            if right == 0 or (left > 0 and left <= right):
+                tmp[i] = i - left
+            elif left == 0 or (right > 0 and left > right):
+                tmp[i] = i + right
+    for i in range(n):
+        if tmp[i] >= 0:
+            if i < invalid_num:
+                start, end = 0, i + invalid_num
+            elif i > n - invalid_num - 1:
+                start, end = i - invalid_num, n - 1
+            else:
+                start, end = i - invalid_num, i + invalid_num
+            lonely = all(tmp[j] != -1 for j in range(start, end + 1))
+            src[i] = -1 if lonely else tmp[i]
+    return src
+
+
+def association(records, counts, frame_numbers=None, max_num_per_video: int = 200, min_length: int = 10,
+                objects=None, predicates=None):
+    """`association()` of lib/utils.py:461-526 for ONE video whose per-frame triplets are the gathered
+    `records [F,100,13]`, `counts [F]` (video order; see `shard.all_gather_triplets`): fills frames without predictions,
+    runs the greedy association on the device, keeps relations of at least `min_length` frames, sorts them by score
+    (descending, stable) and returns the first `max_num_per_video` as the reference's dictionaries.  `objects` /
+    `predicates` map class ids to names as lib/utils.py:34-35 does; without them the ids stay."""
+    records = records if isinstance(records, torch.Tensor) else torch.as_tensor(np.asarray(records, np.float32))
+    records = records.float().cuda() if not records.is_cuda else records.float()
+    cnt_h = [int(c) for c in (counts.tolist() if isinstance(counts, torch.Tensor) else list(counts))]
+    F, K = records.shape[0], records.shape[1]
+    if F == 0 or all(c == 0 for c in cnt_h):
+        return []
+    src = _fill_empty_frames(cnt_h)
+    fnos = list(range(F)) if frame_numbers is None else [int(x) for x in frame_numbers]
+    rel_id, order, info, score, num = ops.greedy_association(records, cnt_h, fnos, src, max_traj=100)
+    n = int(num.item())
+    rel_id, order = rel_id.cpu().numpy(), order.cpu().numpy()
+    info, score = info[:n].cpu().numpy(), score[:n].cpu().numpy()
+    rec = records.cpu().numpy().astype(np.float64)
+    keep = [r for r in range(n) if info[r, 5] >= min_length]
+    keep.sort(key=lambda r: score[r], reverse=True)                  # lib/utils.py:522 (stable, like list.sort)
+    keep = keep[:max_num_per_video]
+    members = {r: [] for r in keep}
+    for f in range(F):
+        row = rel_id[f]
+        for j in np.nonzero(row >= 0)[0]:
+            r = int(row[j])
+            if r in members:
+                members[r].append(rec[src[f], order[f, j]])
+    out = []
+    for r in keep:
+        m = members[r]
+        s, p, o = int(info[r, 2]), int(info[r, 3]), int(info[r, 4])
+        out.append({"triplet": [objects[s] if objects is not None else s, predicates[p] if predicates is not None else p,
+                                objects[o] if objects is not None else o],
+                    "score": float(score[r]), "duration": [int(info[r, 0]), int(info[r, 1])],
+                    "sub_traj": [x[4:8].tolist() for x in m], "obj_traj": [x[8:12].tolist() for x in m],
+                    "rel_idex": [int(x[12]) for x in m]})
+    return out

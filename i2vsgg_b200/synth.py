@@ -215,3 +215,58 @@ def vrd_params(seed: int = 1234, args: VrdArgs | None = None, pool: int = 7) -> 
 def prd_vectors(seed: int, num_relations: int = 132) -> np.ndarray:
     """GloVe stand-in [n_rel, 300] ~ N(0,1)."""
     return np.random.default_rng(seed).standard_normal((num_relations, 300), dtype=np.float32)
+
+
+def clip_records(seed: int, frames: int = 40, tracks: int = 12, clutter: int = 8, top_k: int = 100, empty=()):
+    """Per-frame triplet records of a clip as `i2v_triplet_topk` writes them: [frames, top_k, 13] fp32 =
+    (conf, cls_s, rel, cls_o, sub box, obj box, pair idx) and counts [frames].  `tracks` relation tracks drift by a random
+    walk (consecutive boxes overlap well above IoU 0.5), start / stop / drop out, and share a small label set so that label
+    equality alone does not decide a match; `clutter` random predictions per frame never line up.  Rows are in random
+    order with unique confidences; the frame positions in `empty` have no predictions (lib/utils.py:470-518)."""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros((frames, top_k, 13), np.float32)
+    cnt = np.zeros((frames,), np.int32)
+    labels = [(int(rng.integers(1, 4)), int(rng.integers(0, 3)), int(rng.integers(1, 4))) for _ in range(tracks)]
+    start = rng.integers(0, max(1, frames // 3), tracks)
+    stop = np.minimum(frames, start + rng.integers(5, frames, tracks))
+    base = rng.uniform(0.2, 0.9, tracks)
+
+    def box():
+        x1, y1 = rng.uniform(0, 800), rng.uniform(0, 450)
+        return np.array([x1, y1, x1 + rng.uniform(60, 200), y1 + rng.uniform(60, 150)])
+
+    sb = np.stack([box() for _ in range(tracks)])
+    ob = np.stack([box() for _ in range(tracks)])
+    used = set()
+    for f in range(frames):
+        sb += rng.normal(0, 4.0, sb.shape)
+        ob += rng.normal(0, 4.0, ob.shape)
+        if f in empty:
+            continue
+        rows = []
+        for t in range(tracks):
+            if start[t] <= f < stop[t] and rng.random() > 0.08:
+                rows.append((base[t] + rng.normal(0, 0.03), labels[t], sb[t].copy(), ob[t].copy()))
+        for _ in range(clutter):
+            rows.append((rng.uniform(0.01, 0.95), (int(rng.integers(1, 4)), int(rng.integers(0, 3)), int(rng.integers(1, 4))),
+                         box(), box()))
+        rng.shuffle(rows)
+        for j, (c, (s, p, o), b1, b2) in enumerate(rows[:top_k]):
+            c32 = np.float32(min(max(c, 1e-4), 0.9999))
+            while float(c32) in used:                      # unique confidences: every sort is unambiguous
+                c32 = np.nextafter(c32, np.float32(1))
+            used.add(float(c32))
+            rec[f, j] = [c32, s, p, o, *b1.astype(np.float32), *b2.astype(np.float32), float(rng.integers(0, 4032))]
+        cnt[f] = min(len(rows), top_k)
+    return rec, cnt
+
+
+def records_to_frame_relations(rec, cnt, frame_numbers=None):
+    """The list test_net_SGG_emb.py:209 builds for one video: [[fno, [[conf, [s,p,o], [sub box, obj box], rel idx], ...]], ...]."""
+    out = []
+    for f in range(rec.shape[0]):
+        fno = f if frame_numbers is None else int(frame_numbers[f])
+        preds = [[float(r[0]), [float(r[1]), float(r[2]), float(r[3])], [[float(v) for v in r[4:8]], [float(v) for v in r[8:12]]],
+                  int(r[12])] for r in rec[f, : int(cnt[f])]]
+        out.append([fno, preds])
+    return out

@@ -199,6 +199,20 @@ size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim);
 int i2v_rel_scores(const float* x, const float* prd, float* scores, int num_pairs, int num_rel, int emb_dim,
                    int apply_softmax, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- 10. Temporal association (lib/utils.py:134-182 greedy_relational_association) ---- */
+/* records [F, top_k, 13] fp32 as written by i2v_triplet_topk (all-gathered into video order), counts [F] int32.
+ * frame_numbers [F] ascending (NULL: 0..F-1); source_frame [F] (NULL: identity) lets a frame position use another
+ * frame's records (-1: none), which is how lib/utils.py:470-518 fills frames without predictions.
+ * For frame position f and its j-th prediction in descending confidence: order[f,j] = record row, rel_id[f,j] = the
+ * relation (numbered in creation order) it started or extended, -1 past the frame's predictions.
+ * rel_info [F*top_k, 6] int32 = (first frame number, end frame number, s, p, o, length), rel_score [F*top_k] double =
+ * mean confidence (numpy's pairwise float64 sum), num_rel [1].  top_k <= 128; max_traj = predictions kept per frame. */
+size_t i2v_association_workspace_bytes(int frames, int top_k);
+int i2v_greedy_association(const float* records, const int* counts, const int* frame_numbers, const int* source_frame,
+                           int frames, int top_k, int max_traj, int* rel_id, int* order, int* rel_info,
+                           double* rel_score, int* num_rel, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
