@@ -208,13 +208,13 @@ def run_ours(args):
     # ---- end to end through host buffers
     e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
     for _ in range(min(args.warmup, 2) if e_steps else 0):
-        pipe.host_step(cls_h, reg_h, info_h, feat_h, grad_h)
+        pipe.host_step(cls_h, reg_h, info_h, feat_h, grad_h, chunk_frames=args.e2e_chunk)
     barrier()
     with sampler:
         start2, end2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start2.record()
         for _ in range(e_steps):
-            pipe.host_step(cls_h, reg_h, info_h, feat_h, grad_h)
+            pipe.host_step(cls_h, reg_h, info_h, feat_h, grad_h, chunk_frames=args.e2e_chunk)
         end2.record()
         barrier()
     e2e_ms = reduce_max(start2.elapsed_time(end2))
@@ -243,6 +243,8 @@ def run_ours(args):
                          "other": {k: {"achieved": alg[k] / (stage_ms[k] * 1e-3) / 1e9,
                                        "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / peak} for k in alg}},
         }
+        if not args.no_projection:
+            line["projection"] = projection_side_measurement(dev)
         if not args.no_cpu and world >= 1:
             from oracle import oracle
             threads = oracle.default_threads()
@@ -260,6 +262,35 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def projection_side_measurement(dev):
+    """Outside the timed step: the relation head's dominant GEMM (fc6, 64 objects + 2016 distinct union boxes = 2080 rows
+    x 50176 -> 4096, bf16 on tcgen05) against the measured cuBLAS bf16 peak.  CUDA events, 3 warm-up + 10 launches."""
+    import torch
+    from i2vsgg_b200 import ops
+    m, n, k = 2080, 4096, 50176
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0
+    x = torch.randn((m, k), device=dev).bfloat16()
+    w = (torch.randn((n, k), device=dev) * 0.01).bfloat16()
+    b = torch.zeros((n,), device=dev)
+    y = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.linear(x, w, b, relu=True, out=y)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        ops.linear(x, w, b, relu=True, out=y)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+    return {"kernel": "linear_tcgen05_kernel (fc6 of vrd.forward, SURVEY 8 a19)", "shape": [m, n, k], "dtype": "bf16",
+            "ms": ms, "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                   "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(peaks_path)
+                                   else "fallback (B200_PROFILING.md)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +299,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per copy/compute chunk of the host-buffer leg")
+    ap.add_argument("--no-projection", action="store_true", help="skip the relation-head side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
