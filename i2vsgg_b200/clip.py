@@ -27,21 +27,22 @@ class ClipRunner:
         rep1, inv1 = sgg.unordered_pairs(N, dev)
         U = rep1.numel()
         ixs_l, ixo_l, rel_l, mask_l = [], [], [], []
+        first = torch.arange(N, device=dev) * (N - 1)               # the first pair whose subject is object i
         for f in range(F):
             ixs, ixo, rel, masks = sgg.build_pairs(boxes[f], self.im_h, self.im_w, device=dev)
             rel[:, 0] = float(f)                                     # RoI rows carry the frame index of the group
             ixs_l.append(ixs + f * N)
             ixo_l.append(ixo + f * N)
             rel_l.append(rel)
-            mask_l.append(masks)
+            mask_l.append(masks[first, 0])                           # the N object masks (channel 0 = subject)
         rois = torch.cat([torch.arange(F, device=dev, dtype=torch.float32).repeat_interleave(N)[:, None],
                           boxes.reshape(F * N, 4)], 1)
         offs = torch.arange(F, device=dev)
         rep = (rep1[None, :] + offs[:, None] * P).reshape(-1)
         inv = (inv1[None, :] + offs[:, None] * U).reshape(-1)
         ixs, ixo = torch.cat(ixs_l), torch.cat(ixo_l)
-        scores, _ = self.head(fmap, rois, torch.cat(rel_l), torch.cat(mask_l), None, ixs, ixo, return_numpy=False,
-                              rel_unique=(rep, inv))
+        scores, _ = self.head(fmap, rois, torch.cat(rel_l), None, None, ixs, ixo, return_numpy=False,
+                              rel_unique=(rep, inv), obj_masks=torch.cat(mask_l))
         rec = torch.empty((F, self.top_k, shard.RECORD_WIDTH), dtype=torch.float32, device=dev)
         cnt = torch.empty((F,), dtype=torch.int32, device=dev)
         for f in range(F):

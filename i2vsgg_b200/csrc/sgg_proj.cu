@@ -113,6 +113,44 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
     }
 }
 
+
+// conv_lo[0] for ordered pairs without the im2col of 4032 x 2 masks (resnet_SGG_emb.py:107,182): a pair's two input
+// channels are the masks of its subject and its object, and a convolution is linear in its input channels, so
+//     conv(pair)[pos][oc] = S[subject][pos][oc] + S[object][pos][C + oc] + bias[oc]
+// with S[obj][pos][0..C) / [C..2C) the single-channel convolutions of the object's mask with the subject / object half of
+// the kernel (one small FC launch over N objects instead of P pairs).  This kernel does the add, the ReLU and the bf16
+// rounding, 8 output channels (16 bytes) per thread; out is NHWC [P, positions, C].
+__global__ void __launch_bounds__(256) pair_conv1_kernel(const float* __restrict__ S, const int64_t* __restrict__ ixs,
+                                                         const int64_t* __restrict__ ixo, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int64_t total8, int num_obj,
+                                                         int positions, int C, int relu) {
+    const int chunks = C / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const int64_t pp = i / chunks;
+        const int pos = (int)(pp % positions);
+        const int64_t p = pp / positions;
+        const int64_t a = ixs[p], b = ixo[p];
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = bias ? __ldg(bias + ch * 8 + j) : 0.f;
+        if (a >= 0 && a < num_obj) {
+            const float4* s = reinterpret_cast<const float4*>(S + ((size_t)a * positions + pos) * 2 * C + ch * 8);
+            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+        }
+        if (b >= 0 && b < num_obj) {
+            const float4* s = reinterpret_cast<const float4*>(S + ((size_t)b * positions + pos) * 2 * C + C + ch * 8);
+            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+        }
+        __nv_bfloat16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(relu ? fmaxf(v[j], 0.f) : v[j]);
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<uint4*>(o);
+    }
+}
+
 }  // namespace
 }  // namespace i2v
 
@@ -185,4 +223,18 @@ extern "C" int i2v_gather_rows_bf16(const void* src, const int64_t* idx, void* o
                                                                   static_cast<__nv_bfloat16*>(out), total8, num_src, cols / 8,
                                                                   lds, ldo);
     return check_launch("gather_rows_kernel");
+}
+
+extern "C" int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
+                                   int num_obj, int num_pairs, int positions, int channels, int relu, cudaStream_t stream) {
+    I2V_REQUIRE(num_obj >= 0 && num_pairs >= 0 && positions >= 1 && channels >= 8 && channels % 8 == 0,
+                "pair_conv1: bad shape (channels must be a multiple of 8)");
+    if (num_pairs == 0) return I2V_OK;
+    I2V_REQUIRE(obj_maps && ixs && ixo && out, "pair_conv1: null pointer");
+    I2V_REQUIRE(((uintptr_t)obj_maps & 15) == 0 && ((uintptr_t)out & 15) == 0, "pair_conv1: 16-byte aligned buffers needed");
+    int64_t total8 = (int64_t)num_pairs * positions * (channels / 8);
+    pair_conv1_kernel<<<grid_for(total8, 256, 16), 256, 0, stream>>>(obj_maps, ixs, ixo, bias,
+                                                                     static_cast<__nv_bfloat16*>(out), total8, num_obj,
+                                                                     positions, channels, relu);
+    return check_launch("pair_conv1_kernel");
 }

@@ -103,10 +103,14 @@ class vrd(nn.Module):
         return self
 
     # ------------------------------------------------------------------ forward
-    def forward(self, fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2, return_numpy: bool = True, rel_unique=None):
+    def forward(self, fmap, boxes, rel_boxes, SpatialFea, classes, ix1, ix2, return_numpy: bool = True, rel_unique=None,
+                obj_masks=None):
         """`rel_unique=(rep, inverse)` (see `i2vsgg_b200.sgg.unordered_pairs`) tells the head that rel_boxes[inverse[p]]
         repeats rel_boxes[rep]: the union rows are then pooled and pushed through fc6 / fc7 / fc8 once per distinct box and
-        fanned out afterwards -- bit-identical to the full computation, half the work for ordered pairs."""
+        fanned out afterwards -- bit-identical to the full computation, half the work for ordered pairs.
+        `obj_masks` [N,32,32] (spatial_type 2) promises SpatialFea[p] == [obj_masks[ix1[p]], obj_masks[ix2[p]]], which is
+        how faster_rcnn_SGG_emb.py:649-656 builds it; conv_lo's first layer then runs once per object instead of once per
+        pair (same sums in a different fp32 order) and SpatialFea is not read at all."""
         if self.training:
             raise NotImplementedError("i2vsgg_b200 vrd implements the inference path; call .eval() first "
                                       "(training mode applies dropout, resnet_SGG_emb.py:148-149)")
@@ -153,8 +157,11 @@ class vrd(nn.Module):
             self.fc_lov(ops.cast_bf16(sp), out=fusion[:, col:col + 256])
             col += 256
         elif self.args.spatial_type == 2:                                                   # :175-179
-            sp = _dev(SpatialFea, dev).reshape(n_pair, 2, 32, 32).contiguous()
-            lo = self.conv_lo[0](sp, "nchw")
+            if obj_masks is not None:
+                lo = self.conv_lo[0].forward_pairs(_dev(obj_masks, dev).reshape(n_obj, 32, 32).contiguous(), ix1, ix2)
+            else:
+                sp = _dev(SpatialFea, dev).reshape(n_pair, 2, 32, 32).contiguous()
+                lo = self.conv_lo[0](sp, "nchw")
             lo = self.conv_lo[1](lo, "nhwc")
             lo = self.conv_lo[2](lo, "nhwc")
             self.fc_lov(lo.view(n_pair, -1), out=fusion[:, col:col + 256])

@@ -59,7 +59,32 @@ class Conv2d(nn.Module):
         ops.cast_bf16(w.permute(0, 2, 3, 1).reshape(o, k).contiguous(), buf[:, :k])
         self._w, self._kp = buf, kp
         self._b = b.contiguous()
+        self._w_pair = None
         return self
+
+    def forward_pairs(self, obj_x, ixs, ixo):
+        """This layer applied to P two-channel inputs whose channels are `obj_x[ixs[p]]` and `obj_x[ixo[p]]`
+        (obj_x [N,H,W]): the convolution is linear in its input channels, so each OBJECT map is convolved once with
+        either half of the kernel and a pair is the sum of two rows plus the bias.  -> NHWC bf16 [P,OH,OW,out]."""
+        if self._w is None or self._w.device != obj_x.device:
+            self.prepare()
+        o, kh = self.conv.out_channels, self.conv.kernel_size[0]
+        if self.conv.in_channels != 2:
+            raise ValueError("forward_pairs needs a two-channel convolution")
+        if getattr(self, "_w_pair", None) is None or self._w_pair.device != obj_x.device:
+            taps = kh * kh
+            kp = (taps + 7) // 8 * 8
+            w = self._w[:, : 2 * taps].float().view(o, taps, 2)            # (ky, kx, c) order of prepare()
+            wp = torch.zeros((2 * o, kp), dtype=torch.bfloat16, device=obj_x.device)
+            wp[:o, :taps] = w[:, :, 0].bfloat16()                          # subject half (exact: already bf16 values)
+            wp[o:, :taps] = w[:, :, 1].bfloat16()                          # object half
+            self._w_pair, self._kp_pair = wp, kp
+        n, h, wd = obj_x.shape
+        patches, (_, oh, ow) = ops.im2col_bf16(obj_x.reshape(n, 1, h, wd).contiguous(), kh, self.conv.stride[0],
+                                               self.conv.padding[0], "nchw", ld=self._kp_pair)
+        maps = ops.linear(patches, self._w_pair, None, relu=False, out_dtype=torch.float32)       # [N*OH*OW, 2*out]
+        y = ops.pair_conv1_bf16(maps.view(n, oh * ow, 2 * o), ixs, ixo, self._b, relu=self.relu is not None)
+        return y.view(-1, oh, ow, o)
 
     def forward(self, x, layout: str):
         """x [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`'nhwc'`) -> NHWC bf16 [N,OH,OW,out]: im2col rows + one FC launch."""

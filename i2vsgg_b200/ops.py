@@ -397,3 +397,19 @@ def greedy_association(records, counts, frame_numbers=None, source_frame=None, m
                                          _p(rel_id), _p(order), _p(info), _p(score), _p(num), _p(ws), ws.numel(),
                                          _stream()), "i2v_greedy_association")
     return rel_id, order, info, score, num
+
+
+def pair_conv1_bf16(obj_maps, ixs, ixo, bias, relu: bool = True):
+    """obj_maps [N, positions, 2C] fp32 (per-object single-channel convolutions, subject half then object half) ->
+    relu(obj_maps[ixs][..., :C] + obj_maps[ixo][..., C:] + bias) as NHWC bf16 [P, positions, C]."""
+    obj_maps = _f32(obj_maps, "obj_maps")
+    N, positions, c2 = obj_maps.shape
+    C = c2 // 2
+    ixs, ixo = ixs.long().contiguous(), ixo.long().contiguous()
+    P = ixs.numel()
+    out = torch.empty((P, positions, C), dtype=torch.bfloat16, device=obj_maps.device)
+    b = None if bias is None else _f32(bias, "bias")
+    with torch.cuda.device(obj_maps.device):
+        check(load().i2v_pair_conv1_bf16(_p(obj_maps), _p(ixs), _p(ixo), _p(b), _p(out), N, P, positions, C,
+                                         int(bool(relu)), _stream()), "i2v_pair_conv1_bf16")
+    return out

@@ -188,6 +188,12 @@ int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int heigh
  * [P, 2E] with pitch ldo; obj [N,E] fp32, ixs/ixo [P] int64. */
 int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,
                        int num_pairs, int emb_dim, long long ldo, cudaStream_t stream);
+/* First layer of conv_lo for ordered pairs (resnet_SGG_emb.py:107,182): a pair's two mask channels are the masks of
+ * its subject and object, so conv(pair) = S[subject][.., 0:C] + S[object][.., C:2C] + bias, where obj_maps
+ * [N, positions, 2C] fp32 holds the two single-channel convolutions of every OBJECT mask (one small FC launch).
+ * out [P, positions, C] bf16 (NHWC), ReLU when `relu`. */
+int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
+                        int num_obj, int num_pairs, int positions, int channels, int relu, cudaStream_t stream);
 /* out[p] = src[idx[p]] for bf16 rows (cols % 8 == 0; pitches in elements, multiples of 8).  Used to fan the rows computed
  * once per UNORDERED pair back out to both orderings: the union boxes of (i,j) and (j,i) are the same box
  * (resnet_SGG_emb.py:240-244 is symmetric), so their pooled / fc6 / fc7 / fc8 rows are identical. */

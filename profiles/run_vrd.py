@@ -34,7 +34,8 @@ def main():
     def frame():
         ixs, ixo, rel, masks = sgg.build_pairs(torch.from_numpy(det).cuda(), synth.IM_H, synth.IM_W)
         uniq = None if a.full else sgg.unordered_pairs(a.det)
-        return net(fmap, boxes, rel, masks, classes, ixs, ixo, return_numpy=False, rel_unique=uniq)
+        om = None if a.full else masks[torch.arange(a.det, device="cuda") * (a.det - 1), 0]
+        return net(fmap, boxes, rel, masks, classes, ixs, ixo, return_numpy=False, rel_unique=uniq, obj_masks=om)
 
     for _ in range(2):
         frame()

@@ -168,6 +168,27 @@ def test_vrd_unordered_pair_shortcut_is_bit_identical(orc):
     assert torch.equal(s0, s1) and torch.equal(f0, f1)
 
 
+def test_vrd_object_mask_path_matches_pair_mask_path(orc):
+    """conv_lo's first layer from per-object masks (linear in the input channels) against the im2col of every pair."""
+    args = synth.VrdArgs(vrd_in_channels=32, vrd_hidden=256)
+    params = synth.vrd_params(21, args)
+    net = build(args, params, synth.prd_vectors(5, args.num_relations))
+    fmap = synth.feature_map(31, 1, 32)
+    boxes, rel, masks, classes, ixs, ixo = frame_inputs(orc, 34, 10)
+    obj_masks = np.stack([masks[i * 9, 0] for i in range(10)])
+    assert all(np.array_equal(masks[p], np.stack([obj_masks[ixs[p]], obj_masks[ixo[p]]])) for p in range(90))
+    s0, f0 = net(fmap, boxes, rel, masks, classes, ixs, ixo, return_numpy=False)
+    s1, f1 = net(fmap, boxes, rel, None, classes, ixs, ixo, return_numpy=False, obj_masks=obj_masks)
+    # same bf16 operands, the two halves of each sum are accumulated separately: one bf16 rounding flip at most per value
+    assert float((f0 - f1).abs().max()) <= 5e-3 * float(f0.abs().max())
+    assert float((s0 / s1 - 1).abs().max()) <= 5e-3
+    # the first layer itself: equal up to fp32 association before the bf16 rounding
+    a = net.conv_lo[0](torch.from_numpy(masks).cuda(), "nchw").float()
+    b = net.conv_lo[0].forward_pairs(torch.from_numpy(obj_masks).cuda(), torch.from_numpy(ixs).cuda(),
+                                     torch.from_numpy(ixo).cuda()).float()
+    assert float((a - b).abs().max()) <= 2 ** -7 * float(a.abs().max())
+
+
 def test_vrd_refuses_training_mode_and_cpu():
     from i2vsgg_b200.model.faster_rcnn.resnet_SGG_emb import vrd
     args = synth.VrdArgs(vrd_in_channels=16, vrd_hidden=64)
