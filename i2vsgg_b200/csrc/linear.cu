@@ -4,7 +4,7 @@
 // fc8, so_vis_embeddings, fc_so, fc_lov, fc_fusion, fc_rel; FC = nn.Linear + optional ReLU, lib/model/faster_rcnn/utils.py:48-60).
 // x is K-major (rows of activations), W is nn.Linear's [out, in] layout, i.e. K-major as well.
 //
-// One CTA computes one 128 x 256 output tile:
+// One CTA computes one 128 x 256 output tile (128 x 128 when N <= 128):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the x tile (128 rows) and the W tile (256 rows), one
 //               128-byte swizzled k-block (64 bf16 / 32 tf32) per pipeline stage, completion on an mbarrier;
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=32 bytes per instruction) straight
@@ -20,14 +20,21 @@
 namespace i2v {
 namespace {
 
-constexpr int kBM = 128, kBN = 256, kStages = 4;
+constexpr int kBM = 128;
 constexpr int kRowBytes = 128;                    // one swizzle row of a k-block
 constexpr int kABytes = kBM * kRowBytes;          // 16 KB
-constexpr int kBBytes = kBN * kRowBytes;          // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+// Output tile width BN = 256 (4 stages x 48 KB) for the wide layers, 128 (3 stages x 32 KB) when N <= 128 so that half
+// of every MMA is not spent on zero padding (conv_lo's 128-channel layer has M = 258 048 rows).
+template <int BN>
+struct Tile {
+    static constexpr int kBN = BN;
+    static constexpr int kBBytes = BN * kRowBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = BN == 256 ? 4 : 3;    // 3 x 32 KB: two CTAs per SM, one's epilogue under the other's MMAs
+    static constexpr int kTmemCols = BN;          // power of two >= 32
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,12 +110,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // KIND 0: bf16 operands (64 elements per k-block), KIND 1: fp32 operands read as tf32 (32 elements per k-block).
-template <int KIND>
+template <int KIND, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
     linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                           const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
                           int y_bf16, int relu) {
     constexpr int ELEMS = (KIND == 0) ? 64 : 32;
+    constexpr int kBN = Tile<BN>::kBN, kStages = Tile<BN>::kStages, kStageBytes = Tile<BN>::kStageBytes;
+    constexpr int kTmemCols = Tile<BN>::kTmemCols;
     // instruction descriptor: D = fp32, A/B format (1 = bf16 under kind::f16, 2 = tf32), both K-major, N >> 3, M >> 4
     constexpr uint32_t FMT = (KIND == 0) ? 1u : 2u;
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -263,49 +272,69 @@ __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __r
 }
 
 constexpr int kScoreWarps = 8;
+constexpr int kScoreRows = 4;       // pair rows per warp: every predicate-embedding load feeds four dot products
 __global__ void __launch_bounds__(kScoreWarps * 32)
     rel_score_kernel(const float* __restrict__ x, const float* __restrict__ prdn, float* __restrict__ scores, int P, int R,
                      int E, int apply_softmax) {
-    extern __shared__ float sc_smem[];   // [warps][E] normalised x row, [warps][R] similarities
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int row = blockIdx.x * kScoreWarps + warp;
-    if (row >= P) return;
-    float* xs = sc_smem + (size_t)warp * E;
-    float* sim = sc_smem + (size_t)kScoreWarps * E + (size_t)warp * R;
-    const float* xr = x + (size_t)row * E;
-    float acc = 0.f;
-    for (int i = lane; i < E; i += 32) {
-        float v = xr[i];
-        xs[i] = v;
-        acc += v * v;
+    extern __shared__ float sc_smem[];   // [warps][rows][E] normalised x rows, [warps][rows][R] similarities
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * kScoreWarps + warp) * kScoreRows;
+    if (row0 >= P) return;
+    float* xs = sc_smem + (size_t)warp * kScoreRows * E;
+    float* sim = sc_smem + (size_t)kScoreWarps * kScoreRows * E + (size_t)warp * kScoreRows * R;
+#pragma unroll
+    for (int q = 0; q < kScoreRows; ++q) {
+        const int row = min(row0 + q, P - 1);            // a ragged tail recomputes the last row (never stored)
+        const float* xr = x + (size_t)row * E;
+        float acc = 0.f;
+        for (int i = lane; i < E; i += 32) {
+            float v = xr[i];
+            xs[q * E + i] = v;
+            acc += v * v;
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+        for (int i = lane; i < E; i += 32) xs[q * E + i] *= inv;
     }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
     __syncwarp();
     for (int r = 0; r < R; ++r) {
         const float* p = prdn + (size_t)r * E;
-        float d = 0.f;
-        for (int i = lane; i < E; i += 32) d += (xs[i] * inv) * __ldg(p + i);
-        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0) sim[r] = d;
+        float d[kScoreRows];
+#pragma unroll
+        for (int q = 0; q < kScoreRows; ++q) d[q] = 0.f;
+        for (int i = lane; i < E; i += 32) {
+            const float w = __ldg(p + i);
+#pragma unroll
+            for (int q = 0; q < kScoreRows; ++q) d[q] = fmaf(xs[q * E + i], w, d[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kScoreRows; ++q) {
+            for (int o = 16; o; o >>= 1) d[q] += __shfl_xor_sync(0xffffffffu, d[q], o);
+            if (lane == 0) sim[q * R + r] = d[q];
+        }
     }
     __syncwarp();
-    float* out = scores + (size_t)row * R;
-    if (!apply_softmax) {
-        for (int r = lane; r < R; r += 32) out[r] = sim[r];
-        return;
+    for (int q = 0; q < kScoreRows; ++q) {
+        const int row = row0 + q;
+        if (row >= P) break;
+        float* out = scores + (size_t)row * R;
+        float* sq = sim + q * R;
+        if (!apply_softmax) {
+            for (int r = lane; r < R; r += 32) out[r] = sq[r];
+            continue;
+        }
+        float mx = -INFINITY;
+        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, sq[r]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            float e = expf(sq[r] - mx);
+            sq[r] = e;
+            sum += e;
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int r = lane; r < R; r += 32) out[r] = sq[r] / sum;
     }
-    float mx = -INFINITY;
-    for (int r = lane; r < R; r += 32) mx = fmaxf(mx, sim[r]);
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int r = lane; r < R; r += 32) {
-        float e = expf(sim[r] - mx);
-        sim[r] = e;
-        sum += e;
-    }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    for (int r = lane; r < R; r += 32) out[r] = sim[r] / sum;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -368,17 +397,21 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
                 "linear_forward: x and W need 16-byte aligned bases and row pitches (TMA)");
     alignas(64) CUtensorMap map_x, map_w;
     I2V_TRY(make_map(&map_x, x, kind, M, K, ldx, kBM));
-    I2V_TRY(make_map(&map_w, w, kind, N, K, ldw, kBN));
-    dim3 grid((unsigned)ceil_div(N, kBN), (unsigned)ceil_div(M, kBM));
-    if (kind == 0) {
-        auto kern = linear_tcgen05_kernel<0>;
-        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        kern<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, out_dtype == I2V_DT_BF16, relu);
-    } else {
-        auto kern = linear_tcgen05_kernel<1>;
-        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        kern<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, out_dtype == I2V_DT_BF16, relu);
-    }
+    const int bn = N <= 128 ? 128 : 256;
+    I2V_TRY(make_map(&map_w, w, kind, N, K, ldw, bn));
+    dim3 grid((unsigned)ceil_div(N, bn), (unsigned)ceil_div(M, kBM));
+    const int yb = out_dtype == I2V_DT_BF16;
+#define I2V_LAUNCH_LINEAR(KIND, BN)                                                                                   \
+    do {                                                                                                              \
+        auto kern = linear_tcgen05_kernel<KIND, BN>;                                                                  \
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BN>::kSmemBytes)); \
+        kern<<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb, relu);        \
+    } while (0)
+    if (kind == 0 && bn == 256) I2V_LAUNCH_LINEAR(0, 256);
+    else if (kind == 0) I2V_LAUNCH_LINEAR(0, 128);
+    else if (bn == 256) I2V_LAUNCH_LINEAR(1, 256);
+    else I2V_LAUNCH_LINEAR(1, 128);
+#undef I2V_LAUNCH_LINEAR
     return check_launch("linear_tcgen05_kernel");
 }
 
@@ -410,10 +443,10 @@ extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, i
     float* prdn = static_cast<float*>(workspace);
     l2_normalize_rows_kernel<<<ceil_div(num_rel, 8), 256, 0, stream>>>(prd, prdn, num_rel, emb_dim);
     I2V_TRY(check_launch("l2_normalize_rows_kernel"));
-    size_t smem = (size_t)kScoreWarps * ((size_t)emb_dim + num_rel) * sizeof(float);
+    size_t smem = (size_t)kScoreWarps * kScoreRows * ((size_t)emb_dim + num_rel) * sizeof(float);
     I2V_REQUIRE(smem <= (size_t)kMaxSmemPerCta, "rel_scores: emb_dim + num_rel too large for shared memory");
     I2V_CUDA_TRY(cudaFuncSetAttribute(rel_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rel_score_kernel<<<ceil_div(num_pairs, kScoreWarps), kScoreWarps * 32, smem, stream>>>(x, prdn, scores, num_pairs,
+    rel_score_kernel<<<ceil_div(num_pairs, kScoreWarps * kScoreRows), kScoreWarps * 32, smem, stream>>>(x, prdn, scores, num_pairs,
                                                                                           num_rel, emb_dim, apply_softmax);
     return check_launch("rel_score_kernel");
 }

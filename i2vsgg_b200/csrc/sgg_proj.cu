@@ -85,6 +85,31 @@ __global__ void __launch_bounds__(256) im2col8_kernel(const InT* __restrict__ in
     }
 }
 
+// The same 16-byte-chunk mapping for a contiguous NHWC bf16 input with the geometry known at compile time (conv_lo's
+// second layer: 96 channels, 5x5, stride 2, pad 2, 16x16 -> 8x8): every division is by a constant and the row pitch is
+// exactly KH*KW*C, which takes the index arithmetic from ~100 to ~25 instructions per chunk.
+template <int C, int K, int STRIDE, int PAD, int H, int W>
+__global__ void __launch_bounds__(256) im2col8_fixed_kernel(const __nv_bfloat16* __restrict__ in,
+                                                            __nv_bfloat16* __restrict__ out, int64_t total8) {
+    constexpr int OH = (H + 2 * PAD - K) / STRIDE + 1, OW = (W + 2 * PAD - K) / STRIDE + 1;
+    constexpr int CPT = C / 8, TAPS = K * K, CHUNKS = TAPS * CPT;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total8;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int chunk = (int)(idx % CHUNKS);
+        const int64_t row = idx / CHUNKS;
+        const int c8 = chunk % CPT, tap = chunk / CPT;
+        const int kx = tap % K, ky = tap / K;
+        const int pos = (int)(row % (OH * OW));
+        const int64_t n = row / (OH * OW);
+        const int ox = pos % OW, oy = pos / OW;
+        const int y = oy * STRIDE - PAD + ky, x = ox * STRIDE - PAD + kx;
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            pk = *reinterpret_cast<const uint4*>(in + ((n * H + y) * W + x) * C + c8 * 8);
+        *reinterpret_cast<uint4*>(out + idx * 8) = pk;
+    }
+}
+
 __global__ void __launch_bounds__(256) pair_rows_kernel(const float* __restrict__ obj, const int64_t* __restrict__ ixs,
                                                         const int64_t* __restrict__ ixo, __nv_bfloat16* __restrict__ out,
                                                         int64_t total, int num_obj, int E, int64_t ldo) {
@@ -173,6 +198,13 @@ extern "C" int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels
     if (ldo % 8 == 0 && ((uintptr_t)out & 15) == 0) {   // 16-byte stores
         int64_t total8 = total / 8;
         int grid8 = grid_for(total8, 256, 16);
+        if (in_dtype == I2V_DT_BF16 && channels == 96 && kernel_h == 5 && kernel_w == 5 && stride == 2 && pad == 2 &&
+            height == 16 && width == 16 && stride_c == 1 && stride_x == 96 && stride_y == 96 * 16 &&
+            stride_n == 96 * 256 && ldo == 2400 && ((uintptr_t)in & 15) == 0) {
+            im2col8_fixed_kernel<96, 5, 2, 2, 16, 16><<<grid8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                                 static_cast<__nv_bfloat16*>(out), total8);
+            return check_launch("im2col8_fixed_kernel");
+        }
         if (in_dtype == I2V_DT_F32) {
             im2col8_kernel<float><<<grid8, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out),
                                                              total8, channels, height, width, stride_n, stride_c, stride_y,
