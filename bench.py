@@ -285,7 +285,7 @@ def projection_side_measurement(dev):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-    return {"kernel": "linear_tcgen05_kernel (fc6 of vrd.forward, SURVEY 8 a19)", "shape": [m, n, k], "dtype": "bf16",
+    return {"kernel": "linear_tcgen05_pair_kernel, cta_group::2 (fc6 of vrd.forward, SURVEY 8 a19)", "shape": [m, n, k], "dtype": "bf16",
             "ms": ms, "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(peaks_path)
                                    else "fallback (B200_PROFILING.md)"}}

@@ -4,7 +4,9 @@
 // fc8, so_vis_embeddings, fc_so, fc_lov, fc_fusion, fc_rel; FC = nn.Linear + optional ReLU, lib/model/faster_rcnn/utils.py:48-60).
 // x is K-major (rows of activations), W is nn.Linear's [out, in] layout, i.e. K-major as well.
 //
-// One CTA computes one 128 x 256 output tile (128 x 128 when N <= 128):
+// Wide layers (N > 128, M > 128) run on CTA pairs (linear_tcgen05_pair_kernel below, cta_group::2, 256 x 256 tiles); the
+// single-CTA kernel serves the rest and is the fallback (I2V_LINEAR_1CTA=1).  One CTA computes one 128 x 256 output tile
+// (128 x 128 when N <= 128):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the x tile (128 rows) and the W tile (256 rows), one
 //               128-byte swizzled k-block (64 bf16 / 32 tf32) per pipeline stage, completion on an mbarrier;
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=32 bytes per instruction) straight
@@ -14,6 +16,7 @@
 // Operands are bf16 (kind::f16) or fp32 consumed as tf32 (kind::tf32); accumulation is fp32 in both.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -109,6 +112,58 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// Accumulator rows -> y: warp quarter q owns TMEM lanes [32 q, +32) = tile rows; 32 columns per tcgen05.ld.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int q, int lane, int row, int n0, const float* __restrict__ bias,
+                                              void* __restrict__ y, int M, int N, long long ldy, int y_bf16, int relu) {
+        const bool vec_ok = y_bf16 ? ((ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
+                                   : ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            const int col0 = n0 + ch * 32;
+            if (col0 >= N) break;                      // uniform
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+            if (row < M) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(v[j]);
+                    if (bias != nullptr && col0 + j < N) t += __ldg(bias + col0 + j);
+                    f[j] = relu ? fmaxf(t, 0.f) : t;
+                }
+                if (y_bf16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * ldy + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(y) + (size_t)row * ldy + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = f[j];
+                    }
+                }
+            }
+        }
+}
+
 // KIND 0: bf16 operands (64 elements per k-block), KIND 1: fp32 operands read as tf32 (32 elements per k-block).
 template <int KIND, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -192,56 +247,152 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum, 0);
         tc_fence_after();
-        const bool vec_ok = y_bf16 ? ((ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
-                                   : ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
-#pragma unroll 1
-        for (int ch = 0; ch < kBN / 32; ++ch) {
-            const int col0 = n0 + ch * 32;
-            if (col0 >= N) break;                      // uniform
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-            if (row < M) {
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = __uint_as_float(v[j]);
-                    if (bias != nullptr && col0 + j < N) t += __ldg(bias + col0 + j);
-                    f[j] = relu ? fmaxf(t, 0.f) : t;
-                }
-                if (y_bf16) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * ldy + col0;
-                    if (vec_ok && col0 + 32 <= N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&p0);
-                            pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&p2);
-                            pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                            *reinterpret_cast<uint4*>(dst + j) = pk;
-                        }
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __float2bfloat16_rn(f[j]);
-                    }
-                } else {
-                    float* dst = reinterpret_cast<float*>(y) + (size_t)row * ldy + col0;
-                    if (vec_ok && col0 + 32 <= N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = f[j];
-                    }
-                }
-            }
-        }
+        epilogue_rows<kBN>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- CTA-pair variant
+// Two CTAs of a cluster (one TPC) compute a 256 x 256 tile with tcgen05.mma.cta_group::2: CTA r holds the x rows
+// [128 r, +128) and the W rows [128 r, +128) of the tile, the leader's single thread issues one M = 256 MMA that reads A
+// from both shared memories and either half of B from its owner, and each CTA ends up with its own 128 accumulator rows
+// in its own tensor memory.  Per k-block a CTA moves 32 KB instead of 48 KB through L2 and shared memory for the same
+// flops, which is what the single-CTA kernel is bound by (19 GB of tile traffic for fc6 = 14.5 TB/s at 78 % of peak).
+constexpr int kPairBBytes = 128 * kRowBytes;                       // this CTA's half of the W tile
+constexpr int kPairStageBytes = kABytes + kPairBBytes;             // 32 KB
+constexpr size_t pair_smem_bytes(int stages) { return (size_t)stages * kPairStageBytes + 1024 + 256; }
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                        // shared::cluster address of the same offset in CTA 0
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* sdst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(leader_bar) & kPeerMask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on `bar` in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int KIND, int kPairStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    linear_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                               const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
+                               int y_bf16, int relu) {
+    constexpr int ELEMS = (KIND == 0) ? 64 : 32;
+    constexpr uint32_t FMT = (KIND == 0) ? 1u : 2u;
+    // D = fp32, A/B format, K-major, N = 256 (>> 3), M = 256 (>> 4)
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr int kTmemCols = 256;
+
+    extern __shared__ uint8_t raw_smem[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kPairStages * kPairStageBytes);
+    uint64_t* empty = full + kPairStages;
+    uint64_t* accum = empty + kPairStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int m0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * 128;   // this CTA's 128 rows of x
+    const int n0 = blockIdx.y * 256;                                 // the pair's 256 columns
+    const int kblocks = (K + ELEMS - 1) / ELEMS;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(full + s, 1);      // the leader's arrive.expect_tx covers both CTAs' bytes (used in CTA 0 only)
+            mbar_init(empty + s, 1);     // one multicast commit per use
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                  // both CTAs' barriers are initialised before any remote arrive / TMA completion
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kPairStages;
+                const unsigned round = (unsigned)(kb / kPairStages);
+                mbar_wait(empty + s, (round & 1u) ^ 1u);
+                // Only the leader arrives: its expect_tx announces the bytes of BOTH CTAs.  The peer's loads can complete
+                // first (the transaction count goes negative for a while), but the phase cannot flip before the leader's
+                // arrival, and the peer cannot run a stage ahead because its empty barrier follows the leader's MMAs.  A
+                // remote arrive per k-block from the peer would cost a cluster-scope release fence (~1500 cycles here).
+                if (leader) mbar_expect_tx(full + s, 2 * kPairStageBytes);
+                uint8_t* a = smem + (size_t)s * kPairStageBytes;
+                tma_load_2d_pair(a, &map_x, kb * ELEMS, m0, full + s);
+                tma_load_2d_pair(a + kABytes, &map_w, kb * ELEMS, n0 + (int)rank * 128, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kPairStages;
+                const unsigned round = (unsigned)(kb / kPairStages);
+                mbar_wait(full + s, round & 1u);
+                tc_fence_after();
+                const uint32_t a = smem_u32(smem + (size_t)s * kPairStageBytes);
+                const uint64_t adesc = umma_desc(a), bdesc = umma_desc(a + kABytes);
+#pragma unroll
+                for (int k = 0; k < kRowBytes / 32; ++k) {
+                    const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                    if (KIND == 0) {
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_base),
+                            "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(IDESC), "r"(acc)
+                            : "memory");
+                    } else {
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_base),
+                            "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(IDESC), "r"(acc)
+                            : "memory");
+                    }
+                }
+                tc_commit_pair(empty + s);
+            }
+            tc_commit_pair(accum);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        epilogue_rows<256>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                  // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
                      : "memory");
     }
 }
@@ -398,6 +549,24 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
     alignas(64) CUtensorMap map_x, map_w;
     I2V_TRY(make_map(&map_x, x, kind, M, K, ldx, kBM));
     const int bn = N <= 128 ? 128 : 256;
+    static const bool pair_off = getenv("I2V_LINEAR_1CTA") != nullptr;
+    if (bn == 256 && M > 128 && !pair_off) {
+        // CTA pairs: every CTA loads its own 128 x rows and 128 of the tile's 256 W rows
+        I2V_TRY(make_map(&map_w, w, kind, N, K, ldw, 128));
+        dim3 grid2(2u * (unsigned)ceil_div(M, 256), (unsigned)ceil_div(N, 256));
+        const int yb2 = out_dtype == I2V_DT_BF16;
+        constexpr int kPairStages = 6;
+        if (kind == 0) {
+            auto kern = linear_tcgen05_pair_kernel<0, kPairStages>;
+            I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu);
+        } else {
+            auto kern = linear_tcgen05_pair_kernel<1, kPairStages>;
+            I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu);
+        }
+        return check_launch("linear_tcgen05_pair_kernel");
+    }
     I2V_TRY(make_map(&map_w, w, kind, N, K, ldw, bn));
     dim3 grid((unsigned)ceil_div(N, bn), (unsigned)ceil_div(M, kBM));
     const int yb = out_dtype == I2V_DT_BF16;
