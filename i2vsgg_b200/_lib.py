@@ -49,6 +49,7 @@ SIGNATURES = {
     "i2v_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp]),
     "i2v_im2col_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _ll, _vp]),
     "i2v_pair_rows_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "i2v_conv2d_nhwc_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _i, _i, _vp]),
     "i2v_pair_conv1_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "i2v_gather_rows_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _vp]),
     "i2v_association_workspace_bytes": (_sz, [_i, _i]),

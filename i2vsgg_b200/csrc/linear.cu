@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* map, 
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -165,11 +172,22 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int q, int lan
 }
 
 // KIND 0: bf16 operands (64 elements per k-block), KIND 1: fp32 operands read as tf32 (32 elements per k-block).
-template <int KIND, int BN>
+// Implicit-GEMM convolution (CONV): x is an NHWC activation seen through a 4-D tensor map (channels, x, y, image) whose
+// element strides are the convolution's stride; k-block kb is channel chunk kb % chunks of filter tap kb / chunks, and the
+// 128 tile rows are `rows_per_image` output positions of 128 / rows_per_image consecutive images.  The TMA zero-fills the
+// padding border and the channel padding, so no patch matrix is ever written.
+struct ConvGeom {
+    int chunks;          // 64-channel chunks per tap
+    int kw;              // filter width (taps per filter row)
+    int pad;
+    int rows_per_image;  // OH * OW
+};
+
+template <int KIND, int BN, bool CONV = false>
 __global__ void __launch_bounds__(kThreads, 1)
     linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                           const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
-                          int y_bf16, int relu) {
+                          int y_bf16, int relu, ConvGeom cg = ConvGeom{}) {
     constexpr int ELEMS = (KIND == 0) ? 64 : 32;
     constexpr int kBN = Tile<BN>::kBN, kStages = Tile<BN>::kStages, kStageBytes = Tile<BN>::kStageBytes;
     constexpr int kTmemCols = Tile<BN>::kTmemCols;
@@ -218,7 +236,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(empty + s, (round & 1u) ^ 1u);
                 mbar_expect_tx(full + s, kStageBytes);
                 uint8_t* a = smem + (size_t)s * kStageBytes;
-                tma_load_2d(a, &map_x, kb * ELEMS, m0, full + s);
+                if (CONV) {
+                    const int tap = kb / cg.chunks, chunk = kb - tap * cg.chunks;
+                    const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
+                    tma_load_4d(a, &map_x, chunk * ELEMS, kx - cg.pad, ky - cg.pad, m0 / cg.rows_per_image, full + s);
+                } else {
+                    tma_load_2d(a, &map_x, kb * ELEMS, m0, full + s);
+                }
                 tma_load_2d(a + kABytes, &map_w, kb * ELEMS, n0, full + s);
             }
         }
@@ -424,11 +448,21 @@ __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __r
 
 constexpr int kScoreWarps = 8;
 constexpr int kScoreRows = 4;       // pair rows per warp: every predicate-embedding load feeds four dot products
+// STAGED: the normalised predicate embeddings [R][E] sit in shared memory for the whole CTA (R*E*4 = 158 KB at 132 x 300);
+// otherwise every dot product pulls them from L2 and the kernel is latency-bound on those loads.
+template <bool STAGED>
 __global__ void __launch_bounds__(kScoreWarps * 32)
     rel_score_kernel(const float* __restrict__ x, const float* __restrict__ prdn, float* __restrict__ scores, int P, int R,
                      int E, int apply_softmax) {
-    extern __shared__ float sc_smem[];   // [warps][rows][E] normalised x rows, [warps][rows][R] similarities
+    extern __shared__ __align__(16) float sc_smem[];   // [warps][rows][E] x rows, [warps][rows][R] similarities, ([R][E])
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* pr = prdn;
+    if (STAGED) {
+        float* ps = sc_smem + (size_t)kScoreWarps * kScoreRows * (E + R);
+        for (int i = threadIdx.x; i < R * E; i += kScoreWarps * 32) ps[i] = __ldg(prdn + i);
+        __syncthreads();
+        pr = ps;
+    }
     const int row0 = (blockIdx.x * kScoreWarps + warp) * kScoreRows;
     if (row0 >= P) return;
     float* xs = sc_smem + (size_t)warp * kScoreRows * E;
@@ -449,12 +483,12 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
     }
     __syncwarp();
     for (int r = 0; r < R; ++r) {
-        const float* p = prdn + (size_t)r * E;
+        const float* p = pr + (size_t)r * E;
         float d[kScoreRows];
 #pragma unroll
         for (int q = 0; q < kScoreRows; ++q) d[q] = 0.f;
         for (int i = lane; i < E; i += 32) {
-            const float w = __ldg(p + i);
+            const float w = p[i];
 #pragma unroll
             for (int q = 0; q < kScoreRows; ++q) d[q] = fmaf(xs[q * E + i], w, d[q]);
         }
@@ -574,7 +608,7 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
     do {                                                                                                              \
         auto kern = linear_tcgen05_kernel<KIND, BN>;                                                                  \
         I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BN>::kSmemBytes)); \
-        kern<<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb, relu);        \
+        kern<<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb, relu, ConvGeom{}); \
     } while (0)
     if (kind == 0 && bn == 256) I2V_LAUNCH_LINEAR(0, 256);
     else if (kind == 0) I2V_LAUNCH_LINEAR(0, 128);
@@ -614,8 +648,69 @@ extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, i
     I2V_TRY(check_launch("l2_normalize_rows_kernel"));
     size_t smem = (size_t)kScoreWarps * kScoreRows * ((size_t)emb_dim + num_rel) * sizeof(float);
     I2V_REQUIRE(smem <= (size_t)kMaxSmemPerCta, "rel_scores: emb_dim + num_rel too large for shared memory");
-    I2V_CUDA_TRY(cudaFuncSetAttribute(rel_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rel_score_kernel<<<ceil_div(num_pairs, kScoreWarps * kScoreRows), kScoreWarps * 32, smem, stream>>>(x, prdn, scores, num_pairs,
-                                                                                          num_rel, emb_dim, apply_softmax);
+    size_t staged = smem + (size_t)num_rel * emb_dim * sizeof(float);
+    int grid = ceil_div(num_pairs, kScoreWarps * kScoreRows);
+    if (staged <= (size_t)kMaxSmemPerCta && grid >= 8) {
+        I2V_CUDA_TRY(cudaFuncSetAttribute(rel_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+        rel_score_kernel<true><<<grid, kScoreWarps * 32, staged, stream>>>(x, prdn, scores, num_pairs, num_rel, emb_dim,
+                                                                          apply_softmax);
+    } else {
+        I2V_CUDA_TRY(cudaFuncSetAttribute(rel_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rel_score_kernel<false><<<grid, kScoreWarps * 32, smem, stream>>>(x, prdn, scores, num_pairs, num_rel, emb_dim,
+                                                                         apply_softmax);
+    }
     return check_launch("rel_score_kernel");
+}
+
+// conv_lo's strided layers as an implicit GEMM (resnet_SGG_emb.py:107-110): x [N,H,W,C] bf16 NHWC, w [O, KH*KW*Cp] bf16
+// with every tap's channels padded to Cp = 64 * ceil(C / 64), y [N*OH*OW, O] (NHWC of the next layer).
+extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
+                                       int channels, int out_channels, int kernel, int stride, int pad, long long ldw,
+                                       long long ldy, int out_dtype, int relu, cudaStream_t stream) {
+    I2V_REQUIRE(n >= 0 && height >= 1 && width >= 1 && channels >= 1 && out_channels >= 1 && kernel >= 1 && stride >= 1 &&
+                    pad >= 0,
+                "conv2d_nhwc: bad shape");
+    I2V_REQUIRE(out_dtype == I2V_DT_BF16 || out_dtype == I2V_DT_F32, "conv2d_nhwc: out_dtype %d", out_dtype);
+    const int OH = (height + 2 * pad - kernel) / stride + 1, OW = (width + 2 * pad - kernel) / stride + 1;
+    const int rows = OH * OW, chunks = ceil_div(channels, 64), K = kernel * kernel * chunks * 64;
+    const bool ok = OH >= 1 && OW >= 1 && rows <= kBM && kBM % rows == 0 && channels % 8 == 0 && out_channels <= 128 &&
+                    OW * stride <= 256 && OH * stride <= 256 && ldw >= K && (ldw * 2) % 16 == 0 &&
+                    ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0;
+    if (!ok) {
+        set_error("conv2d_nhwc: needs OH*OW dividing 128, C %% 8 == 0, at most 128 output channels and 16-byte aligned rows");
+        return I2V_ERR_UNSUPPORTED;
+    }
+    if (n == 0) return I2V_OK;
+    I2V_REQUIRE(x && w && y, "conv2d_nhwc: null pointer");
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error("conv2d_nhwc: cuTensorMapEncodeTiled is not available from this driver");
+        return I2V_ERR_CUDA;
+    }
+    alignas(64) CUtensorMap map_x, map_w;
+    {
+        const int per_tile = kBM / rows;
+        cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n};
+        cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)width * channels * 2,
+                                 (cuuint64_t)height * width * channels * 2};
+        // with an element stride s the box extent counts traversed positions: OW samples span OW * s of them
+        cuuint32_t box[4] = {64, (cuuint32_t)(OW * stride), (cuuint32_t)(OH * stride), (cuuint32_t)per_tile};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = fn(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("conv2d_nhwc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return I2V_ERR_INVALID;
+        }
+    }
+    I2V_TRY(make_map(&map_w, w, 0, out_channels, K, ldw, 128));
+    const int M = n * rows;
+    ConvGeom cg{chunks, kernel, pad, rows};
+    dim3 grid(1u, (unsigned)ceil_div(M, kBM));
+    auto kern = linear_tcgen05_kernel<0, 128, true>;
+    I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<128>::kSmemBytes));
+    kern<<<grid, kThreads, Tile<128>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, out_channels, K, ldy,
+                                                           out_dtype == I2V_DT_BF16, relu, cg);
+    return check_launch("linear_tcgen05_kernel<conv>");
 }

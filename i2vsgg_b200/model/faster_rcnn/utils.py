@@ -60,6 +60,11 @@ class Conv2d(nn.Module):
         self._w, self._kp = buf, kp
         self._b = b.contiguous()
         self._w_pair = None
+        # the implicit-GEMM layout: every tap's channels padded to a multiple of 64 (one or more whole k-blocks per tap)
+        cp = (c + 63) // 64 * 64
+        taps = torch.zeros((o, kh * kw, cp), dtype=torch.bfloat16, device=w.device)
+        taps[:, :, :c] = buf[:, :k].view(o, kh * kw, c)
+        self._w_taps = taps.view(o, kh * kw * cp)
         return self
 
     def forward_pairs(self, obj_x, ixs, ixo):
@@ -91,6 +96,12 @@ class Conv2d(nn.Module):
         if self._w is None or self._w.device != x.device:
             self.prepare()
         kh = self.conv.kernel_size[0]
+        st, pd = self.conv.stride[0], self.conv.padding[0]
+        if layout == "nhwc" and x.dtype == torch.bfloat16 and x.is_contiguous() and st > 1:
+            oh, ow = (x.size(1) + 2 * pd - kh) // st + 1, (x.size(2) + 2 * pd - kh) // st + 1
+            if 128 % (oh * ow) == 0 and x.size(3) % 8 == 0 and self.conv.out_channels <= 128:
+                # strided layer: implicit GEMM, the 4-D TMA map reads the patches straight out of the activation
+                return ops.conv2d_nhwc(x, self._w_taps, self._b, kh, st, pd, relu=self.relu is not None)
         if (layout == "nhwc" and x.dtype == torch.bfloat16 and x.size(1) == kh and x.size(2) == kh
                 and self.conv.padding[0] == 0 and self._kp == kh * kh * x.size(3) and x.is_contiguous()):
             # the kernel covers the whole map: the NHWC activation row already is the (ky, kx, c) patch

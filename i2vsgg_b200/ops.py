@@ -413,3 +413,21 @@ def pair_conv1_bf16(obj_maps, ixs, ixo, bias, relu: bool = True):
         check(load().i2v_pair_conv1_bf16(_p(obj_maps), _p(ixs), _p(ixo), _p(b), _p(out), N, P, positions, C,
                                          int(bool(relu)), _stream()), "i2v_pair_conv1_bf16")
     return out
+
+
+def conv2d_nhwc(x, weight_taps, bias, kernel: int, stride: int, pad: int, relu: bool = True, out_dtype=torch.bfloat16):
+    """Implicit-GEMM convolution on tcgen05: x [N,H,W,C] bf16 NHWC, weight_taps [O, kernel*kernel*Cp] bf16 (taps in
+    (ky, kx) order, channels of each tap padded to Cp = 64*ceil(C/64)) -> [N,OH,OW,O].  Raises I2VError (unsupported) for
+    shapes it does not take; callers fall back to im2col_bf16 + linear."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or not x.is_contiguous():
+        raise _lib.I2VError("conv2d_nhwc: expected a contiguous NHWC bf16 CUDA tensor")
+    n, h, w, c = x.shape
+    o = weight_taps.size(0)
+    oh, ow = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
+    out = torch.empty((n, oh, ow, o), dtype=out_dtype, device=x.device)
+    b = None if bias is None else _f32(bias, "bias")
+    with torch.cuda.device(x.device):
+        check(load().i2v_conv2d_nhwc_forward(_p(x), _p(weight_taps), _p(b), _p(out), n, h, w, c, o, kernel, stride, pad,
+                                             weight_taps.stride(0), o, _TORCH_DT[out_dtype], int(bool(relu)), _stream()),
+              "i2v_conv2d_nhwc_forward")
+    return out

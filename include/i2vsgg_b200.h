@@ -188,6 +188,14 @@ int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int heigh
  * [P, 2E] with pitch ldo; obj [N,E] fp32, ixs/ixo [P] int64. */
 int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,
                        int num_pairs, int emb_dim, long long ldo, cudaStream_t stream);
+/* Strided convolution as an implicit GEMM on tcgen05 (conv_lo's second layer, resnet_SGG_emb.py:108): x [N,H,W,C] bf16
+ * NHWC is read through a 4-D TMA map with the convolution's element strides and zero-filled borders, so no patch matrix
+ * is written.  w [O, K*K*Cp] bf16, taps in (ky, kx) order with each tap's channels padded to Cp = 64*ceil(C/64), row
+ * pitch ldw; y [N*OH*OW, O] with pitch ldy = the next layer's NHWC input.  Needs OH*OW dividing 128, C % 8 == 0 and
+ * O <= 128; I2V_ERR_UNSUPPORTED otherwise (use i2v_im2col_bf16 + i2v_linear_forward). */
+int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
+                            int channels, int out_channels, int kernel, int stride, int pad, long long ldw,
+                            long long ldy, int out_dtype, int relu, cudaStream_t stream);
 /* First layer of conv_lo for ordered pairs (resnet_SGG_emb.py:107,182): a pair's two mask channels are the masks of
  * its subject and object, so conv(pair) = S[subject][.., 0:C] + S[object][.., C:2C] + bias, where obj_maps
  * [N, positions, 2C] fp32 holds the two single-channel convolutions of every OBJECT mask (one small FC launch).

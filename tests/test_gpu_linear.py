@@ -150,3 +150,22 @@ def test_im2col_matches_unfold(ops, layout, c, h, k, stride, pad, dtype):
     assert torch.equal(got[:, :kk], want) and torch.all(got[:, kk:] == 0)
     got1, _ = ops.im2col_bf16(xin, k, stride, pad, layout, ld=kk + 1 if (kk + 1) % 8 else kk + 3)   # scalar-store path
     assert torch.equal(got1[:, :kk], want)
+
+
+@pytest.mark.parametrize("c,o,h,k,stride,pad", [(96, 128, 16, 5, 2, 2), (64, 32, 16, 3, 2, 1), (8, 128, 8, 3, 1, 1)])
+def test_conv2d_nhwc_implicit_gemm_matches_torch(ops, c, o, h, k, stride, pad):
+    """The 4-D TMA map (element strides = conv stride, zero-filled borders and channel padding) against F.conv2d in
+    float64 on the same bf16 operands."""
+    g = torch.Generator(device="cuda").manual_seed(c + o)
+    n = 37
+    x = torch.randn((n, c, h, h), device="cuda", generator=g).bfloat16()
+    w = (torch.randn((o, c, k, k), device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn((o,), device="cuda", generator=g)
+    cp = (c + 63) // 64 * 64
+    taps = torch.zeros((o, k * k, cp), device="cuda", dtype=torch.bfloat16)
+    taps[:, :, :c] = w.permute(0, 2, 3, 1).reshape(o, k * k, c)
+    y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), taps.view(o, -1), b, k, stride, pad, relu=True,
+                        out_dtype=torch.float32)
+    want = torch.relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad))
+    assert y.shape == (n, want.shape[2], want.shape[3], o)
+    assert float((y.permute(0, 3, 1, 2).double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
