@@ -270,3 +270,22 @@ def records_to_frame_relations(rec, cnt, frame_numbers=None):
                   int(r[12])] for r in rec[f, : int(cnt[f])]]
         out.append([fno, preds])
     return out
+
+
+def proposals_and_gt(seed: int, batch: int = 2, num_rois: int = 300, num_gt: int = 6, max_gt: int = 20, num_classes: int = 21):
+    """Inputs of the proposal-target layer: all_rois [B,R,5] (b,x1,y1,x2,y2) and gt_boxes [B,max_gt,5] (x1,y1,x2,y2,label),
+    zero-padded past `num_gt` (config.py MAX_NUM_GT_BOXES style).  A third of the proposals are jittered copies of a
+    ground-truth box (foreground), the rest are random."""
+    rng = np.random.default_rng(seed)
+    gt = np.zeros((batch, max_gt, 5), np.float32)
+    rois_out = np.zeros((batch, num_rois, 5), np.float32)
+    for b in range(batch):
+        x1, y1 = rng.uniform(0, 700, num_gt), rng.uniform(0, 400, num_gt)
+        w, h = rng.uniform(40, 280, num_gt), rng.uniform(40, 190, num_gt)
+        gt[b, :num_gt] = np.stack([x1, y1, x1 + w, y1 + h, rng.integers(1, num_classes, num_gt)], 1)
+        r = rois(seed * 31 + b, num_rois, batch=1, edge_frac=0.0, degenerate=0)
+        near = rng.integers(0, num_gt, num_rois // 3)
+        r[: num_rois // 3, 1:] = gt[b, near, :4] + rng.normal(0, 6.0, (num_rois // 3, 4))
+        r[:, 0] = b
+        rois_out[b] = r
+    return rois_out, gt

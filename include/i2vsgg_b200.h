@@ -227,6 +227,27 @@ int i2v_greedy_association(const float* records, const int* counts, const int* f
                            double* rel_score, int* num_rel, void* workspace, size_t workspace_bytes,
                            cudaStream_t stream);
 
+/* ---- 11. Proposal targets (lib/model/rpn/proposal_target_layer_cascade.py:33-212) ---- */
+/* bbox_overlaps_batch (bbox_transform.py:215-257) reduced on the fly: rois [B,R,roi_width] (roi_width 5: (b,x1,y1,x2,y2),
+ * 4: (x1,y1,x2,y2)), gt_boxes [B,K,5] (x1,y1,x2,y2,label) -> max_overlaps [B,R], assignment [B,R] (first arg-max),
+ * labels [B,R] = label of the assigned box (may be NULL).  Zero-area gt -> 0, zero-area roi -> -1, as there. */
+int i2v_roi_gt_overlaps(const float* rois, int roi_width, const float* gt_boxes, int batch, int num_rois, int num_gt,
+                        float* max_overlaps, int* assignment, float* labels, cudaStream_t stream);
+/* Per image, in ascending order (torch.nonzero): fg_inds = {i: max >= fg_thresh}, bg_inds = {i: bg_lo <= max < bg_hi}
+ * (both [B,R] int32, only the first counts[b][0] / counts[b][1] entries are written), counts [B,2]. */
+int i2v_fg_bg_select(const float* max_overlaps, int batch, int num_rois, float fg_thresh, float bg_thresh_hi,
+                     float bg_thresh_lo, int* fg_inds, int* bg_inds, int* counts, cudaStream_t stream);
+/* positions [B,S] index INTO fg_inds (first fg_this[b] entries of a row) or bg_inds (the rest), as drawn by the caller
+ * (the reference draws them with numpy, :151-180).  Outputs as _sample_rois_pytorch returns them: rois_out [B,S,5],
+ * labels_out [B,S], targets_out / inside_out / outside_out [B,S,4] (bbox_transform_batch, optional normalisation by
+ * means / stds -- host pointers to four floats each -- and BBOX_INSIDE_WEIGHTS; zero for background). */
+int i2v_proposal_targets_gather(const float* rois, const float* gt_boxes, const int* assignment, const float* labels,
+                                const int* fg_inds, const int* bg_inds, const int* positions, const int* fg_this,
+                                int batch, int num_rois, int num_gt, int rois_per_image, const float* means,
+                                const float* stds, const float* inside_weights, int normalize, float* rois_out,
+                                float* labels_out, float* targets_out, float* inside_out, float* outside_out,
+                                cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

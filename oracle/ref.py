@@ -301,3 +301,20 @@ def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial
     finally:
         torch.Tensor.cuda = old_cuda
     return scores.numpy(), feat
+
+
+def py_proposal_target_layer(all_rois, gt_boxes, num_classes=21, seed=0, overrides=None):
+    """Executes `_ProposalTargetLayer.forward` (lib/model/rpn/proposal_target_layer_cascade.py:33-59) unmodified on CPU
+    tensors after `np.random.seed(seed)`.  Returns the five outputs as numpy arrays."""
+    _py_setup()
+    import torch
+    from model.utils.config import cfg
+    from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+    for k, v in (overrides or {}).items():
+        cfg.TRAIN[k] = v
+    layer = _ProposalTargetLayer(num_classes)
+    np.random.seed(seed)
+    with torch.no_grad():
+        out = layer(torch.from_numpy(np.ascontiguousarray(all_rois, np.float32)),
+                    torch.from_numpy(np.ascontiguousarray(gt_boxes, np.float32)), None)
+    return [o.numpy() for o in out]
