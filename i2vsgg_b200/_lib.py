@@ -56,6 +56,11 @@ SIGNATURES = {
     "i2v_fg_bg_select": (_i, [_vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "i2v_proposal_targets_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp,
                                          _vp, _vp, _vp, _vp, _vp]),
+    "i2v_anchor_overlaps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "i2v_anchor_labels": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _i, _vp, _vp]),
+    "i2v_anchor_disable": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "i2v_anchor_targets_finalize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp,
+                                         _vp]),
     "i2v_association_workspace_bytes": (_sz, [_i, _i]),
     "i2v_greedy_association": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "i2v_rel_scores_workspace_bytes": (_sz, [_i, _i]),

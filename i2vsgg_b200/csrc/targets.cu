@@ -146,6 +146,131 @@ __global__ void __launch_bounds__(256) proposal_target_gather_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ anchor targets
+// `_AnchorTargetLayer` (lib/model/rpn/anchor_target_layer.py:48-193).  Anchor j = (y*W + x)*A + a as in the proposal
+// layer; an anchor is "inside" when it lies within the FIRST image's bounds (:81-84 reads im_info[0] for the whole batch).
+__device__ __forceinline__ float4 grid_anchor(const float* __restrict__ base, int j, int A, int W, int stride) {
+    const int a = j % A, k = j / A;
+    const float sx = (float)((k % W) * stride), sy = (float)((k / W) * stride);
+    return make_float4(base[a * 4] + sx, base[a * 4 + 1] + sy, base[a * 4 + 2] + sx, base[a * 4 + 3] + sy);
+}
+__device__ __forceinline__ bool anchor_inside(const float4 a, float border, float im_w, float im_h) {
+    return a.x >= -border && a.y >= -border && a.z < im_w + border && a.w < im_h + border;
+}
+
+// Pass 1: per inside anchor the max / first arg-max overlap over the image's ground truth (:100), and per ground-truth
+// box the max over anchors (:101) through an integer atomicMax (overlaps of generated anchors are >= 0, where the float
+// order is the order of the bit patterns).  max_ov = -2 marks an outside anchor.
+__global__ void __launch_bounds__(256) anchor_overlap_kernel(const float* __restrict__ base, const float* __restrict__ gt,
+                                                             int total, int A, int W, int stride, int G, float border,
+                                                             float im_w, float im_h, float* __restrict__ max_ov,
+                                                             int* __restrict__ argmax, int* __restrict__ gt_max_bits) {
+    extern __shared__ float s_gt[];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < G * 5; i += blockDim.x) s_gt[i] = gt[(size_t)b * G * 5 + i];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const float4 a = grid_anchor(base, j, A, W, stride);
+    if (!anchor_inside(a, border, im_w, im_h)) {
+        max_ov[(size_t)b * total + j] = -2.f;
+        argmax[(size_t)b * total + j] = 0;
+        return;
+    }
+    float best = -INFINITY;
+    int arg = 0;
+    for (int g = 0; g < G; ++g) {
+        const float ov = overlap(a, make_float4(s_gt[g * 5], s_gt[g * 5 + 1], s_gt[g * 5 + 2], s_gt[g * 5 + 3]));
+        if (ov > best) {
+            best = ov;
+            arg = g;
+        }
+        if (ov > 0.f) atomicMax(gt_max_bits + b * G + g, __float_as_int(ov));
+    }
+    max_ov[(size_t)b * total + j] = best;
+    argmax[(size_t)b * total + j] = arg;
+}
+
+// Pass 2: the label rules of :103-119 (labels as floats: 1 positive, 0 negative, -1 don't care / outside).
+__global__ void __launch_bounds__(256) anchor_label_kernel(const float* __restrict__ base, const float* __restrict__ gt,
+                                                           int total, int A, int W, int stride, int G,
+                                                           const float* __restrict__ max_ov, const int* __restrict__ gt_max_bits,
+                                                           float neg_thresh, float pos_thresh, int clobber,
+                                                           float* __restrict__ labels) {
+    extern __shared__ float s_gt[];      // [G][5] then [G] gt maxima
+    float* s_max = s_gt + G * 5;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < G * 5; i += blockDim.x) s_gt[i] = gt[(size_t)b * G * 5 + i];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float m = __int_as_float(gt_max_bits[b * G + g]);
+        s_max[g] = (m == 0.f) ? 1e-5f : m;                                   // :106
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const float mo = max_ov[(size_t)b * total + j];
+    float label = -1.f;
+    if (mo != -2.f) {
+        const float4 a = grid_anchor(base, j, A, W, stride);
+        bool is_gt_best = false;
+        for (int g = 0; g < G; ++g)
+            is_gt_best |= overlap(a, make_float4(s_gt[g * 5], s_gt[g * 5 + 1], s_gt[g * 5 + 2], s_gt[g * 5 + 3])) == s_max[g];
+        if (!clobber && mo < neg_thresh) label = 0.f;
+        if (is_gt_best) label = 1.f;
+        if (mo >= pos_thresh) label = 1.f;
+        if (clobber && mo < neg_thresh) label = 0.f;
+    }
+    labels[(size_t)b * total + j] = label;
+}
+
+// labels[b][list[b][positions[b][k]]] = -1 for k < n_disable[b]  (:131-145: the sub-sampled anchors become don't-care)
+__global__ void __launch_bounds__(256) anchor_disable_kernel(float* __restrict__ labels, const int* __restrict__ list,
+                                                             const int* __restrict__ positions, const int* __restrict__ n_disable,
+                                                             int total, int max_disable) {
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_disable[b]) return;
+    labels[(size_t)b * total + list[(size_t)b * total + positions[(size_t)b * max_disable + k]]] = -1.f;
+}
+
+// Pass 3: regression targets against the arg-max box (:150), weights (:153-165) and the output layouts of :167-191:
+// labels [B,1,A*H,W], targets / inside / outside [B,4A,H,W].
+__global__ void __launch_bounds__(256) anchor_finalize_kernel(const float* __restrict__ base, const float* __restrict__ gt,
+                                                              int total, int A, int H, int W, int stride, int G,
+                                                              const float* __restrict__ max_ov, const int* __restrict__ argmax,
+                                                              const float* __restrict__ labels, float inside_w,
+                                                              float pos_w, float neg_w, float* __restrict__ labels_out,
+                                                              float* __restrict__ targets_out, float* __restrict__ inside_out,
+                                                              float* __restrict__ outside_out) {
+    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const int a = j % A, k = j / A, x = k % W, y = k / W;
+    const float label = labels[(size_t)b * total + j];
+    labels_out[((size_t)b * A + a) * H * W + (size_t)y * W + x] = label;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (max_ov[(size_t)b * total + j] != -2.f) {
+        const float4 e = grid_anchor(base, j, A, W, stride);
+        const float* g = gt + ((size_t)b * G + argmax[(size_t)b * total + j]) * 5;
+        const float ew = (e.z - e.x) + 1.0f, eh = (e.w - e.y) + 1.0f;
+        const float ecx = e.x + 0.5f * ew, ecy = e.y + 0.5f * eh;
+        const float gw = (g[2] - g[0]) + 1.0f, gh = (g[3] - g[1]) + 1.0f;
+        const float gcx = g[0] + 0.5f * gw, gcy = g[1] + 0.5f * gh;
+        t[0] = (gcx - ecx) / ew;
+        t[1] = (gcy - ecy) / eh;
+        t[2] = logf(gw / ew);
+        t[3] = logf(gh / eh);
+    }
+    const float iw = label == 1.f ? inside_w : 0.f;
+    const float ow = label == 1.f ? pos_w : (label == 0.f ? neg_w : 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const size_t o = ((size_t)b * 4 * A + a * 4 + c) * H * W + (size_t)y * W + x;
+        targets_out[o] = t[c];
+        inside_out[o] = iw;
+        outside_out[o] = ow;
+    }
+}
+
 }  // namespace
 }  // namespace i2v
 
@@ -197,4 +322,64 @@ extern "C" int i2v_proposal_targets_gather(const float* rois, const float* gt_bo
         rois, gt_boxes, assignment, labels, fg_inds, bg_inds, positions, fg_this, batch, num_rois, num_gt, rois_per_image, nm,
         rois_out, labels_out, targets_out, inside_out, outside_out);
     return check_launch("proposal_target_gather_kernel");
+}
+
+extern "C" int i2v_anchor_overlaps(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors, int height,
+                                   int width, int feat_stride, int num_gt, float allowed_border, float im_w, float im_h,
+                                   float* max_overlaps, int* argmax, int* gt_max_bits, cudaStream_t stream) {
+    I2V_REQUIRE(batch >= 0 && num_anchors >= 1 && height >= 1 && width >= 1 && num_gt >= 1, "anchor_overlaps: bad shape");
+    if (batch == 0) return I2V_OK;
+    I2V_REQUIRE(base_anchors && gt_boxes && max_overlaps && argmax && gt_max_bits, "anchor_overlaps: null pointer");
+    const int total = num_anchors * height * width;
+    I2V_CUDA_TRY(cudaMemsetAsync(gt_max_bits, 0, sizeof(int) * (size_t)batch * num_gt, stream));
+    size_t smem = (size_t)num_gt * 5 * sizeof(float);
+    I2V_REQUIRE(smem <= 40 * 1024, "anchor_overlaps: too many ground-truth boxes per image");
+    dim3 grid((unsigned)ceil_div(total, 256), (unsigned)batch);
+    anchor_overlap_kernel<<<grid, 256, smem, stream>>>(base_anchors, gt_boxes, total, num_anchors, width, feat_stride, num_gt,
+                                                      allowed_border, im_w, im_h, max_overlaps, argmax, gt_max_bits);
+    return check_launch("anchor_overlap_kernel");
+}
+
+extern "C" int i2v_anchor_labels(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors, int height,
+                                 int width, int feat_stride, int num_gt, const float* max_overlaps, const int* gt_max_bits,
+                                 float negative_overlap, float positive_overlap, int clobber_positives, float* labels,
+                                 cudaStream_t stream) {
+    I2V_REQUIRE(batch >= 0 && num_anchors >= 1 && height >= 1 && width >= 1 && num_gt >= 1, "anchor_labels: bad shape");
+    if (batch == 0) return I2V_OK;
+    I2V_REQUIRE(base_anchors && gt_boxes && max_overlaps && gt_max_bits && labels, "anchor_labels: null pointer");
+    const int total = num_anchors * height * width;
+    size_t smem = (size_t)num_gt * 6 * sizeof(float);
+    dim3 grid((unsigned)ceil_div(total, 256), (unsigned)batch);
+    anchor_label_kernel<<<grid, 256, smem, stream>>>(base_anchors, gt_boxes, total, num_anchors, width, feat_stride, num_gt,
+                                                    max_overlaps, gt_max_bits, negative_overlap, positive_overlap,
+                                                    clobber_positives, labels);
+    return check_launch("anchor_label_kernel");
+}
+
+extern "C" int i2v_anchor_disable(float* labels, const int* list, const int* positions, const int* n_disable, int batch,
+                                  int total_anchors, int max_disable, cudaStream_t stream) {
+    I2V_REQUIRE(batch >= 0 && total_anchors >= 0 && max_disable >= 0, "anchor_disable: bad shape");
+    if (batch == 0 || max_disable == 0) return I2V_OK;
+    I2V_REQUIRE(labels && list && positions && n_disable, "anchor_disable: null pointer");
+    dim3 grid((unsigned)ceil_div(max_disable, 256), (unsigned)batch);
+    anchor_disable_kernel<<<grid, 256, 0, stream>>>(labels, list, positions, n_disable, total_anchors, max_disable);
+    return check_launch("anchor_disable_kernel");
+}
+
+extern "C" int i2v_anchor_targets_finalize(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors,
+                                           int height, int width, int feat_stride, int num_gt, const float* max_overlaps,
+                                           const int* argmax, const float* labels, float inside_weight,
+                                           float positive_weight, float negative_weight, float* labels_out,
+                                           float* targets_out, float* inside_out, float* outside_out, cudaStream_t stream) {
+    I2V_REQUIRE(batch >= 0 && num_anchors >= 1 && height >= 1 && width >= 1 && num_gt >= 1, "anchor_targets_finalize: bad shape");
+    if (batch == 0) return I2V_OK;
+    I2V_REQUIRE(base_anchors && gt_boxes && max_overlaps && argmax && labels && labels_out && targets_out && inside_out &&
+                    outside_out,
+                "anchor_targets_finalize: null pointer");
+    const int total = num_anchors * height * width;
+    dim3 grid((unsigned)ceil_div(total, 256), (unsigned)batch);
+    anchor_finalize_kernel<<<grid, 256, 0, stream>>>(base_anchors, gt_boxes, total, num_anchors, height, width, feat_stride,
+                                                    num_gt, max_overlaps, argmax, labels, inside_weight, positive_weight,
+                                                    negative_weight, labels_out, targets_out, inside_out, outside_out);
+    return check_launch("anchor_finalize_kernel");
 }

@@ -248,6 +248,30 @@ int i2v_proposal_targets_gather(const float* rois, const float* gt_boxes, const 
                                 float* labels_out, float* targets_out, float* inside_out, float* outside_out,
                                 cudaStream_t stream);
 
+/* ---- 12. Anchor targets (lib/model/rpn/anchor_target_layer.py:48-193) ---- */
+/* Anchor j = (y*W + x)*A + a over the [height, width] RPN map; "inside" anchors lie within [-border, im_w + border) x
+ * [-border, im_h + border) (:81-84, the first image's size for the whole batch).  gt_boxes [B,G,5].
+ * max_overlaps [B,KA] (-2 for outside anchors), argmax [B,KA], gt_max_bits [B,G] (float bits of the per-box maxima). */
+int i2v_anchor_overlaps(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors, int height,
+                        int width, int feat_stride, int num_gt, float allowed_border, float im_w, float im_h,
+                        float* max_overlaps, int* argmax, int* gt_max_bits, cudaStream_t stream);
+/* The label rules of :103-119 -> labels [B,KA] (1 / 0 / -1 as floats). */
+int i2v_anchor_labels(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors, int height, int width,
+                      int feat_stride, int num_gt, const float* max_overlaps, const int* gt_max_bits,
+                      float negative_overlap, float positive_overlap, int clobber_positives, float* labels,
+                      cudaStream_t stream);
+/* labels[b][list[b][positions[b][k]]] = -1 for k < n_disable[b] (:131-145; `list` as written by i2v_fg_bg_select on the
+ * label array, positions [B,max_disable] drawn by the caller with numpy like the reference). */
+int i2v_anchor_disable(float* labels, const int* list, const int* positions, const int* n_disable, int batch,
+                       int total_anchors, int max_disable, cudaStream_t stream);
+/* Regression targets, weights and the output layouts of :150-191: labels_out [B,1,A*H,W], targets_out / inside_out /
+ * outside_out [B,4A,H,W]. */
+int i2v_anchor_targets_finalize(const float* base_anchors, const float* gt_boxes, int batch, int num_anchors, int height,
+                                int width, int feat_stride, int num_gt, const float* max_overlaps, const int* argmax,
+                                const float* labels, float inside_weight, float positive_weight, float negative_weight,
+                                float* labels_out, float* targets_out, float* inside_out, float* outside_out,
+                                cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,3 +318,19 @@ def py_proposal_target_layer(all_rois, gt_boxes, num_classes=21, seed=0, overrid
         out = layer(torch.from_numpy(np.ascontiguousarray(all_rois, np.float32)),
                     torch.from_numpy(np.ascontiguousarray(gt_boxes, np.float32)), None)
     return [o.numpy() for o in out]
+
+
+def py_anchor_target_layer(gt_boxes, im_info, feat_h=38, feat_w=63, seed=0):
+    """Executes `_AnchorTargetLayer.forward` (lib/model/rpn/anchor_target_layer.py:48-193) unmodified on CPU tensors after
+    `np.random.seed(seed)`.  Returns [labels, bbox_targets, inside_weights, outside_weights] as numpy arrays."""
+    _py_setup()
+    import torch
+    from model.utils.config import cfg
+    from model.rpn.anchor_target_layer import _AnchorTargetLayer
+    layer = _AnchorTargetLayer(cfg.FEAT_STRIDE[0], cfg.ANCHOR_SCALES, cfg.ANCHOR_RATIOS)
+    gt = torch.from_numpy(np.ascontiguousarray(gt_boxes, np.float32))
+    score = torch.zeros((gt.shape[0], 18, feat_h, feat_w))
+    np.random.seed(seed)
+    with torch.no_grad():
+        out = layer((score, gt, torch.from_numpy(np.ascontiguousarray(im_info, np.float32)), None))
+    return [o.numpy() for o in out]

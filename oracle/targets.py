@@ -83,3 +83,64 @@ def proposal_target_layer(all_rois, gt_boxes, batch_size=128, fg_fraction=0.25, 
     targets = np.where(pos[..., None], t, F(0)).astype(F)
     inside_w = np.where(pos[..., None], np.asarray(inside, F), F(0)).astype(F)
     return rois_b, labels_b, targets, inside_w, (inside_w > 0).astype(F)
+
+
+def anchor_target_layer(gt_boxes, im_info, base_anchors, feat_h, feat_w, feat_stride=16, neg=0.3, pos=0.7, clobber=False,
+                        fg_fraction=0.5, batchsize=256, inside_weight=1.0, allowed_border=0):
+    """lib/model/rpn/anchor_target_layer.py:48-193 in numpy (float32, the reference's operation order and numpy draws)
+    -> [labels [B,1,A*H,W], targets, inside, outside (each [B,4A,H,W])]."""
+    gt = np.asarray(gt_boxes, F)
+    B, G = gt.shape[:2]
+    A = base_anchors.shape[0]
+    sx, sy = np.meshgrid(np.arange(feat_w) * feat_stride, np.arange(feat_h) * feat_stride)
+    shifts = np.stack([sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel()], 1).astype(F)
+    allan = (np.asarray(base_anchors, F)[None] + shifts[:, None]).reshape(-1, 4)
+    total = allan.shape[0]
+    im_h, im_w = int(im_info[0][0]), int(im_info[0][1])
+    keep = ((allan[:, 0] >= -allowed_border) & (allan[:, 1] >= -allowed_border) & (allan[:, 2] < im_w + allowed_border) &
+            (allan[:, 3] < im_h + allowed_border))
+    inds = np.nonzero(keep)[0]
+    anchors = allan[inds]
+    ov = overlaps_batch(np.broadcast_to(anchors[None], (B,) + anchors.shape), gt)            # :98
+    max_ov, argmax = ov.max(2), ov.argmax(2)
+    gt_max = ov.max(1)
+    labels = np.full((B, len(inds)), -1, F)
+    if not clobber:
+        labels[max_ov < F(neg)] = 0
+    gt_max[gt_max == 0] = F(1e-5)
+    k = (ov == gt_max[:, None, :]).sum(2)
+    if k.sum() > 0:
+        labels[k > 0] = 1
+    labels[max_ov >= F(pos)] = 1
+    if clobber:
+        labels[max_ov < F(neg)] = 0
+    num_fg = int(fg_fraction * batchsize)
+    sum_fg, sum_bg = (labels == 1).sum(1), (labels == 0).sum(1)
+    for i in range(B):
+        if sum_fg[i] > num_fg:
+            fg = np.nonzero(labels[i] == 1)[0]
+            labels[i][fg[np.random.permutation(len(fg))[: len(fg) - num_fg]]] = -1
+        num_bg = batchsize - (labels[i] == 1).sum()
+        if sum_bg[i] > num_bg:
+            bg = np.nonzero(labels[i] == 0)[0]
+            labels[i][bg[np.random.permutation(len(bg))[: len(bg) - num_bg]]] = -1
+    gsel = np.take_along_axis(gt[:, :, :4], argmax[..., None], 1)
+    t = transform_batch(np.broadcast_to(anchors[None], gsel.shape), gsel)
+    inside = np.zeros_like(labels)
+    inside[labels == 1] = F(inside_weight)
+    w = F(1.0 / int((labels[B - 1] >= 0).sum()))                                           # :156-158, the last image
+    outside = np.zeros_like(labels)
+    outside[labels == 1] = w
+    outside[labels == 0] = w
+
+    def unmap(d, fill):
+        out = np.full((B, total) + d.shape[2:], fill, F)
+        out[:, inds] = d
+        return out
+
+    H, W = feat_h, feat_w
+    lab = unmap(labels, -1).reshape(B, H, W, A).transpose(0, 3, 1, 2).reshape(B, 1, A * H, W)
+    tg = unmap(t, 0).reshape(B, H, W, A * 4).transpose(0, 3, 1, 2)
+    iw = np.repeat(unmap(inside, 0)[..., None], 4, 2).reshape(B, H, W, 4 * A).transpose(0, 3, 1, 2)
+    ow = np.repeat(unmap(outside, 0)[..., None], 4, 2).reshape(B, H, W, 4 * A).transpose(0, 3, 1, 2)
+    return [np.ascontiguousarray(a) for a in (lab, tg, iw, ow)]

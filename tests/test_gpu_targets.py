@@ -51,3 +51,19 @@ def test_overlap_reduction_matches_oracle_matrix():
                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "overlaps")
     assert np.array_equal(mx.cpu().numpy(), ov.max(2)) and np.array_equal(am.cpu().numpy(), ov.argmax(2))
     assert float(mx[0, 5]) == -1.0
+
+
+@pytest.mark.parametrize("name", ["a_b2", "a_b3_crowded"])
+def test_anchor_target_layer_equals_reference(name):
+    from i2vsgg_b200.model.rpn.anchor_target_layer import _AnchorTargetLayer
+    from test_oracle_targets import _check_anchor_outputs
+    m = gen()
+    g = np.load(os.path.join(HERE, "golden", "targets_golden.npz"))
+    kw = m.ANCHOR_CASES[name]
+    _, gt = synth.proposals_and_gt(num_rois=30, **kw)
+    layer = _AnchorTargetLayer(16, [8, 16, 32], [0.5, 1, 2])
+    score = torch.zeros((kw["batch"], 18, 38, 63), device="cuda")
+    np.random.seed(m.NP_SEED)
+    out = layer((score, torch.from_numpy(gt).cuda(), torch.from_numpy(synth.im_info(kw["batch"])).cuda(), None))
+    assert out[0].shape == (kw["batch"], 1, 9 * 38, 63) and out[1].shape == (kw["batch"], 36, 38, 63)
+    _check_anchor_outputs([o.cpu().numpy() for o in out], g, name, 2e-6)
