@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--det", type=int, default=64)
     ap.add_argument("--group", type=int, default=4)
+    ap.add_argument("--associate", action="store_true", help="rank 0 also runs the temporal association on the gathered records")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -72,11 +73,21 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ok = rec.shape == (a.frames, 100, 13) and int(cnt.min()) == 100
+    assoc = None
+    if rank == 0 and a.associate:
+        from i2vsgg_b200 import sgg
+        import time
+        sgg.association(rec[:8], cnt[:8])                       # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rels = sgg.association(rec, cnt)
+        assoc = {"ms": 1e3 * (time.perf_counter() - t0), "relations": len(rels),
+                 "longest": max([r["duration"][1] - r["duration"][0] for r in rels] or [0])}
     if rank == 0:
         print(json.dumps({"workload": f"configs[4]: {a.frames}-frame clip, {a.det} detections -> {a.det * (a.det - 1)} pairs per "
                                       f"frame, pair build + vrd.forward + triplet top-100, all-gather of records",
                           "n_gpus": world, "frames": a.frames, "ms": float(ms.item()),
-                          "frames_per_s": a.frames / (float(ms.item()) * 1e-3), "records_ok": bool(ok),
+                          "frames_per_s": a.frames / (float(ms.item()) * 1e-3), "records_ok": bool(ok), "association": assoc,
                           "gather_bytes": int(rec.numel() * 4)}), flush=True)
     if world > 1:
         dist.barrier()
