@@ -54,7 +54,7 @@ __device__ __forceinline__ void lattice_axis(float lo, float hi, int G, int exte
 __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois, int batch, int H, int W, int GH,
                                     int GW, float scale, LatticeRoi* __restrict__ tab, int* __restrict__ roi_batch,
                                     int* __restrict__ counts, PlaneTab* __restrict__ ptab, float ptab_scale,
-                                    BwdTab* __restrict__ btab) {
+                                    BwdTab* __restrict__ btab, int ptab_row_bytes) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= num_rois) return;
     const float* r = rois + (size_t)n * 5;
@@ -99,7 +99,7 @@ __global__ void lattice_prep_kernel(const float* __restrict__ rois, int num_rois
             float we = (sx & 1) ? wr : wl, wo = (sx & 1) ? wl : wr;
             q.xa[p] = make_float4(__int_as_float(even * 64), we, __int_as_float(odd * 64), wo);
             q.xb[p] = make_float4(__int_as_float(odd * 64), wo, __int_as_float(even * 64), we);
-            q.y[p] = make_float4(__int_as_float(t.y.start[p] * 4096), oky ? 1.f - t.y.frac[p] : 0.f,
+            q.y[p] = make_float4(__int_as_float(t.y.start[p] * ptab_row_bytes), oky ? 1.f - t.y.frac[p] : 0.f,
                                  oky ? t.y.frac[p] : 0.f, 0.f);
         }
         ptab[n] = q;
@@ -317,11 +317,12 @@ __device__ __forceinline__ void cp_async_wait() {
 // both orders), so the two halves hit disjoint bank groups in every load: conflict free by construction, and all
 // index math is uniform per half-warp.  Each lane ends up with the P*P outputs of its (RoI, channel); they are staged
 // as [16][P*P] -- contiguous in the NCHW output -- and leave through a TMA bulk store per half.
-constexpr int kPitch = 64;                      // cells per shared-memory row
+// Cells per shared-memory row: 64 for landscape maps (W <= 64, H <= 38 at 16 channels), 40 for portrait ones (W <= 40,
+// H <= 63: a 1000 x 600 frame gives a 63 x 38 map).  Any even pitch keeps "parity of a cell = parity of its column".
 constexpr int kCellBytes = kPlaneK * 4;         // 64 bytes per cell
-constexpr int kRowBytes = kPitch * kCellBytes;  // 4096 bytes per row
+__host__ __device__ constexpr int plane_pitch_for(int W) { return W <= 40 ? 40 : 64; }
 
-template <int P, int POOL>
+template <int P, int POOL, int kPitch>
 __global__ void __launch_bounds__(kPlaneThreads, 1)
     lattice_fwd_plane_kernel(const float* __restrict__ feat, const PlaneTab* __restrict__ ptab,
                              const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ out,
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
     constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
     constexpr int NOUT = P * P;
     constexpr int TILE = kPlaneK * NOUT;  // floats per staged output tile
+    constexpr int kRowBytes = kPitch * kCellBytes;
     constexpr int TABF = (int)(sizeof(PlaneTab) / sizeof(float));
     constexpr int TABV = (int)(sizeof(PlaneTab) / 16);
     static_assert(G <= 8, "tables hold 8 lattice points per axis");
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1)
             const float* g = src + row * W;
             float* d = dst + (size_t)row * kPitch * kPlaneK;
 #pragma unroll 4
-            for (int j = 0; j < kPitch / 2; ++j) {
+            for (int j = 0; 2 * j < W; ++j) {
                 if (2 * j + tdx < W) cp_async4(d + j * 2 * kPlaneK, g + 2 * j);
             }
         }
@@ -780,7 +782,8 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
                                                                      lists ? w.counts : nullptr,
                                                                      (lists && ptab_scale != 0.f && !backward) ? w.ptab : nullptr,
                                                                      ptab_scale,
-                                                                     (lists && ptab_scale != 0.f && backward) ? w.btab : nullptr);
+                                                                     (lists && ptab_scale != 0.f && backward) ? w.btab : nullptr,
+                                                                     plane_pitch_for(W) * kCellBytes);
     I2V_TRY(check_launch("lattice_prep_kernel"));
     if (lists) {
         roi_bucket_kernel<<<batch + 1, 256, 0, stream>>>(w.roi_batch, num_rois, batch + 1, w.counts, w.starts, w.order);
@@ -789,14 +792,14 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
     return I2V_OK;
 }
 
-static size_t plane_fwd_smem_bytes(int H, int P) {
+static size_t plane_fwd_smem_bytes(int H, int W, int P) {
     size_t stage = (size_t)kPlaneWarps * 2 * kPlaneK * P * P;
-    return ((size_t)H * kPitch * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 4 * sizeof(PlaneTab);
+    return ((size_t)H * plane_pitch_for(W) * kPlaneK + stage) * sizeof(float) + (size_t)kPlaneWarps * 4 * sizeof(PlaneTab);
 }
 
 static bool plane_forward_ok(const float* out, int batch, int C, int H, int W, int PH, int PW) {
-    return batch > 0 && PH == 7 && PW == 7 && C % kPlaneK == 0 && H >= 2 && W >= 2 && W <= kPitch &&
-           plane_fwd_smem_bytes(H, 7) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0;
+    return batch > 0 && PH == 7 && PW == 7 && C % kPlaneK == 0 && H >= 2 && W >= 2 && W <= 64 &&
+           plane_fwd_smem_bytes(H, W, 7) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0;
 }
 
 static int plane_split(int ctas) {
@@ -805,17 +808,23 @@ static int plane_split(int ctas) {
     return split;
 }
 
-template <int POOL>
-static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
-                            cudaStream_t stream) {
-    auto kern = lattice_fwd_plane_kernel<7, POOL>;
-    size_t smem = plane_fwd_smem_bytes(H, 7);
+template <int POOL, int PITCH>
+static int launch_plane_fwd_p(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
+                              cudaStream_t stream) {
+    auto kern = lattice_fwd_plane_kernel<7, POOL, PITCH>;
+    size_t smem = plane_fwd_smem_bytes(H, W, 7);
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctiles = C / kPlaneK;
     int split = plane_split(batch * ctiles);
     kern<<<(batch + 1) * ctiles * split, kPlaneThreads, smem, stream>>>(feat, w.ptab, w.order, w.starts, out, batch, C,
                                                                        H, W, split);
     return check_launch("lattice_fwd_plane_kernel");
+}
+template <int POOL>
+static int launch_plane_fwd(const float* feat, const LatticeWs& w, float* out, int batch, int C, int H, int W,
+                            cudaStream_t stream) {
+    if (plane_pitch_for(W) == 40) return launch_plane_fwd_p<POOL, 40>(feat, w, out, batch, C, H, W, stream);
+    return launch_plane_fwd_p<POOL, 64>(feat, w, out, batch, C, H, W, stream);
 }
 
 static size_t plane_bwd_smem_bytes(int H, int W, int P) {

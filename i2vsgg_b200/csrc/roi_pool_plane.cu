@@ -18,7 +18,8 @@ namespace i2v {
 namespace {
 
 constexpr int kK = 16;            // channels per CTA
-constexpr int kPitch = 65;        // cells per shared-memory row (odd: see above)
+// cells per shared-memory row, odd (see above): 65 for landscape maps (W <= 64), 41 for portrait ones (W <= 40, H up to 77)
+__host__ __device__ constexpr int pool_pitch_for(int W) { return W <= 40 ? 41 : 65; }
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kBins = 49;
@@ -41,7 +42,7 @@ __device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bf
 // half-warp 1 rows 1, 3, ... of the bin row: NR/2 loads at compile-time offsets for both halves, plus -- for odd NR -- one
 // more at `tail` (the extra row of half 0; half 1 re-reads its last row, which cannot change a maximum).  No lane-dependent
 // control flow.  Bins tile the columns with at most one shared column, whose value is carried into the next bin.
-template <int NR, typename OutT>
+template <int NR, int kPitch, typename OutT>
 __device__ __forceinline__ void sweep_bin_row(const float* p, int tail, int x, int lo, int hi, int half, OutT* dst) {
     constexpr int kRow2 = 2 * kPitch * kK;
     float v = -FLT_MAX, carry = -FLT_MAX;
@@ -63,7 +64,7 @@ __device__ __forceinline__ void sweep_bin_row(const float* p, int tail, int x, i
     }
 }
 
-template <typename OutT>
+template <typename OutT, int kPitch>
 __global__ void __launch_bounds__(kThreads, 1)
     roi_pool_plane_kernel(const float* __restrict__ feat, const float* __restrict__ rois, OutT* __restrict__ out,
                           int batch, int C, int H, int W, int num_rois, float scale, int64_t ldo, int split) {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     continue;
                 }
                 // half 0 takes rows hs, hs+2, ...; half 1 rows hs+1, hs+3, ...: same column, opposite bank half.
-                // A bin is at most 8 rows tall (H <= 49, checked on the host).
+                // A bin is at most 12 rows tall (H <= 77, checked on the host).
                 const int nr = he - hs;
                 const int myrows = (nr - half + 1) >> 1;
                 constexpr int kRow2 = 2 * kPitch * kK;          // two rows further down, in floats
@@ -147,14 +148,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float* p = rowp + (size_t)x0 * kK;
                     const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;
                     switch (nr) {   // uniform
-                        case 1: sweep_bin_row<1>(p, tail, x0, lo, hi, half, dst); break;
-                        case 2: sweep_bin_row<2>(p, tail, x0, lo, hi, half, dst); break;
-                        case 3: sweep_bin_row<3>(p, tail, x0, lo, hi, half, dst); break;
-                        case 4: sweep_bin_row<4>(p, tail, x0, lo, hi, half, dst); break;
-                        case 5: sweep_bin_row<5>(p, tail, x0, lo, hi, half, dst); break;
-                        case 6: sweep_bin_row<6>(p, tail, x0, lo, hi, half, dst); break;
-                        case 7: sweep_bin_row<7>(p, tail, x0, lo, hi, half, dst); break;
-                        default: sweep_bin_row<8>(p, tail, x0, lo, hi, half, dst); break;
+                        case 1: sweep_bin_row<1, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 2: sweep_bin_row<2, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 3: sweep_bin_row<3, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 4: sweep_bin_row<4, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 5: sweep_bin_row<5, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 6: sweep_bin_row<6, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 7: sweep_bin_row<7, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 8: sweep_bin_row<8, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 9: sweep_bin_row<9, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 10: sweep_bin_row<10, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 11: sweep_bin_row<11, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        default: sweep_bin_row<12, kPitch>(p, tail, x0, lo, hi, half, dst); break;
                     }
                 } else {
 #pragma unroll 1
@@ -179,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-size_t plane_smem_bytes(int H, size_t esz) {
-    return (size_t)H * kPitch * kK * sizeof(float) + (size_t)kWarps * kK * kBins * esz;
+size_t plane_smem_bytes(int H, int W, size_t esz) {
+    return (size_t)H * pool_pitch_for(W) * kK * sizeof(float) + (size_t)kWarps * kK * kBins * esz;
 }
 
 }  // namespace
@@ -190,27 +195,29 @@ int roi_pool_rows_plane(const float* features, const float* rois, void* out, int
                         int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
                         int out_dtype, cudaStream_t stream) {
     const size_t esz = out_dtype == I2V_DT_BF16 ? 2 : 4;
-    const bool ok = pooled_h == 7 && pooled_w == 7 && channels % kK == 0 && width <= kPitch - 1 && height <= 49 &&
+    const bool ok = pooled_h == 7 && pooled_w == 7 && channels % kK == 0 && width <= 64 && height <= 77 &&
                     batch >= 1 &&
-                    plane_smem_bytes(height, esz) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0 &&
+                    plane_smem_bytes(height, width, esz) <= (size_t)kMaxSmemPerCta && ((uintptr_t)out & 15) == 0 &&
                     ((size_t)ldo * esz) % 16 == 0;
     if (!ok) return I2V_ERR_UNSUPPORTED;
     const int ctiles = channels / kK;
     int split = 1;
     while (batch * ctiles * split < 2 * kNumSMs && split * kWarps < num_rois && split < 16) split *= 2;
-    const size_t smem = plane_smem_bytes(height, esz);
+    const size_t smem = plane_smem_bytes(height, width, esz);
     dim3 grid((unsigned)(batch * ctiles * split));
-    if (out_dtype == I2V_DT_BF16) {
-        auto kern = roi_pool_plane_kernel<__nv_bfloat16>;
-        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, stream>>>(features, rois, static_cast<__nv_bfloat16*>(out), batch, channels, height,
-                                               width, num_rois, spatial_scale, ldo, split);
-    } else {
-        auto kern = roi_pool_plane_kernel<float>;
-        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, stream>>>(features, rois, static_cast<float*>(out), batch, channels, height, width,
-                                               num_rois, spatial_scale, ldo, split);
-    }
+#define I2V_LAUNCH_POOL(T, PITCH)                                                                                     \
+    do {                                                                                                              \
+        auto kern = roi_pool_plane_kernel<T, PITCH>;                                                                  \
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        kern<<<grid, kThreads, smem, stream>>>(features, rois, static_cast<T*>(out), batch, channels, height, width,  \
+                                               num_rois, spatial_scale, ldo, split);                                  \
+    } while (0)
+    const bool narrow = pool_pitch_for(width) == 41;
+    if (out_dtype == I2V_DT_BF16 && narrow) I2V_LAUNCH_POOL(__nv_bfloat16, 41);
+    else if (out_dtype == I2V_DT_BF16) I2V_LAUNCH_POOL(__nv_bfloat16, 65);
+    else if (narrow) I2V_LAUNCH_POOL(float, 41);
+    else I2V_LAUNCH_POOL(float, 65);
+#undef I2V_LAUNCH_POOL
     return check_launch("roi_pool_plane_kernel");
 }
 

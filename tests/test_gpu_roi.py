@@ -290,3 +290,34 @@ def test_legacy_launchers(ops, orc):
     pg = torch.full((2, 8, 38, 63), 7.0, device="cuda")
     assert lib.ROIPoolBackwardLaucher(P(cuda(g7)), SCALE, 2, 20, 38, 63, 8, 7, 7, P(r), P(pg), P(pa), s) == 1
     close(pg, orc.roi_pool_backward(g7, rois, wa, feat.shape, 7, 7, SCALE))
+
+
+def _portrait_rois(seed, n, batch):
+    r = synth.rois(seed, n, batch=batch)
+    return np.ascontiguousarray(r[:, [0, 2, 1, 4, 3]])          # swap x and y: boxes of a 1000 x 600 (h x w) frame
+
+
+@pytest.mark.parametrize("pool", ["none", "avg", "max"])
+def test_portrait_maps_stay_on_the_plane_kernels(ops, orc, pool):
+    """A 1000 x 600 frame gives a 63 x 38 map: the plane kernels take it with the 40-cell row pitch (forward) and the
+    orientation-independent plane size (backward) instead of falling back to the gather kernels."""
+    B, C, H, W, N = 2, 32, 63, 38, 80
+    feat = synth.feature_map(300, B, C, H, W)
+    rois = _portrait_rois(301, N, B)
+    want = orc.roi_align_pooled_forward(feat, rois, 7, 7, SCALE, pool, nthreads=8)
+    got = ops.roi_align_forward(cuda(feat), cuda(rois), 7, 7, SCALE, pool, "plane")
+    close(got, want)
+    if pool != "max":
+        g = np.random.default_rng(7).standard_normal((N, C, 7, 7)).astype(np.float32)
+        wantg = orc.roi_align_pooled_backward(g, feat, rois, 7, 7, SCALE, pool, nthreads=8)
+        gotg = ops.roi_align_backward(cuda(g), None, cuda(rois), feat.shape, 7, 7, SCALE, pool, "plane")
+        close(gotg, wantg)
+
+
+def test_portrait_roi_pool_rows(ops):
+    from i2vsgg_b200._lib import ARGMAX_PLANE
+    feat = cuda(synth.feature_map(302, 1, 32, 63, 38))
+    rois = cuda(_portrait_rois(303, 60, 1))
+    want, _ = ops.roi_pool_forward(feat, rois, 7, 7, SCALE, ARGMAX_PLANE)
+    got = ops.roi_pool_rows(feat, rois, 7, 7, SCALE, dtype=torch.float32)
+    assert torch.equal(got, want.reshape(60, -1))
