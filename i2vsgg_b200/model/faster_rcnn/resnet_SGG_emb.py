@@ -164,7 +164,7 @@ class vrd(nn.Module):
                 lo = self.conv_lo[0](sp, "nchw")
             lo = self.conv_lo[1](lo, "nhwc")
             lo = self.conv_lo[2](lo, "nhwc")
-            self.fc_lov(lo.view(n_pair, -1), out=fusion[:, col:col + 256])
+            self.fc_lov(lo.reshape(n_pair, 64), out=fusion[:, col:col + 256])
             col += 256
         x = self.fc_rel(self.fc_fusion(fusion), out_dtype=torch.float32)                    # :190-191
         scores = ops.rel_scores(x, self._prd_emb, softmax=True)                             # :203-219 (eval)

@@ -89,7 +89,7 @@ class Conv2d(nn.Module):
                                                self.conv.padding[0], "nchw", ld=self._kp_pair)
         maps = ops.linear(patches, self._w_pair, None, relu=False, out_dtype=torch.float32)       # [N*OH*OW, 2*out]
         y = ops.pair_conv1_bf16(maps.view(n, oh * ow, 2 * o), ixs, ixo, self._b, relu=self.relu is not None)
-        return y.view(-1, oh, ow, o)
+        return y.view(ixs.numel(), oh, ow, o)
 
     def forward(self, x, layout: str):
         """x [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`'nhwc'`) -> NHWC bf16 [N,OH,OW,out]: im2col rows + one FC launch."""
@@ -105,8 +105,8 @@ class Conv2d(nn.Module):
         if (layout == "nhwc" and x.dtype == torch.bfloat16 and x.size(1) == kh and x.size(2) == kh
                 and self.conv.padding[0] == 0 and self._kp == kh * kh * x.size(3) and x.is_contiguous()):
             # the kernel covers the whole map: the NHWC activation row already is the (ky, kx, c) patch
-            patches, (n, oh, ow) = x.view(x.size(0), -1), (x.size(0), 1, 1)
+            patches, (n, oh, ow) = x.view(x.size(0), kh * kh * x.size(3)), (x.size(0), 1, 1)
         else:
             patches, (n, oh, ow) = ops.im2col_bf16(x, kh, self.conv.stride[0], self.conv.padding[0], layout, ld=self._kp)
         y = ops.linear(patches, self._w, self._b, relu=self.relu is not None, out_dtype=torch.bfloat16)
-        return y.view(n, oh, ow, -1)
+        return y.view(n, oh, ow, self.conv.out_channels)

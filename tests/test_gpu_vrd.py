@@ -222,3 +222,25 @@ def test_clip_runner_groups_frames_without_changing_records(orc):
     scores, _ = head(fmaps[2:3], rois, rel, masks, None, ixs, ixo, return_numpy=False)
     want, wc = ops.triplet_topk(scores, s[2], c[2], b[2], ixs, ixo, shard.TOP_K)
     assert torch.equal(rec1[2], want) and int(cnt1[2]) == int(wc[0])
+
+
+@pytest.mark.parametrize("n_det", [1, 2])
+def test_vrd_tiny_frames(orc, n_det):
+    """One detection has no pair (the reference's detection_output returns None there, lib/utils.py:585-586); two have
+    two.  The head must come back with empty / tiny tensors instead of tripping over zero-sized launches."""
+    from i2vsgg_b200 import sgg
+    args = synth.VrdArgs(vrd_in_channels=32, vrd_hidden=128)
+    net = build(args, synth.vrd_params(4, args), synth.prd_vectors(5, args.num_relations))
+    fmap = synth.feature_map(31, 1, 32)
+    det, classes, _ = synth.detections(36, n_det)
+    boxes = np.concatenate([np.zeros((n_det, 1), np.float32), det], 1)
+    ixs, ixo, rel, masks = sgg.build_pairs(torch.from_numpy(det).cuda(), synth.IM_H, synth.IM_W)
+    scores, feat = net(fmap, boxes, rel, masks, classes, ixs, ixo)
+    p = n_det * (n_det - 1)
+    assert scores.shape == (p, 132) and feat.shape == (p, 300)
+    if p:
+        want_s, want_f = orc.vrd_forward(synth.vrd_params(4, args), synth.prd_vectors(5, args.num_relations), fmap, boxes,
+                                         rel.cpu().numpy(), masks.cpu().numpy(), ixs.cpu().numpy(), ixo.cpu().numpy())
+        np.testing.assert_allclose(scores.cpu().numpy(), want_s, rtol=2e-2, atol=1e-6)
+        s2, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo, rel_unique=sgg.unordered_pairs(n_det))
+        assert torch.equal(s2, scores)
