@@ -54,6 +54,9 @@ class HostPipeline:
         f32 = dict(dtype=torch.float32, device=device)
         self.anchors = torch.from_numpy(synth.BASE_ANCHORS).to(device)
         self.rois = torch.empty((frames, post_nms, 5), **f32)
+        self._rois_pp = [self.rois, torch.empty((frames, post_nms, 5), **f32)]   # ping-pong for the pipelined step
+        self._side = None            # second stream: the next batch's proposal layer
+        self._pending = None         # (buffer index, event) of a proposal launched ahead
         self.counts = torch.empty((frames,), dtype=torch.int32, device=device)
         self.pooled = torch.empty((self.N, channels, pooled, pooled), **f32)
         self.grad_in = torch.empty((frames, channels, feat_h, feat_w), **f32)
@@ -91,6 +94,47 @@ class HostPipeline:
     def device_step(self, cls_prob, bbox_pred, im_info, features, grad_out, timer: StageTimer | None = None):
         self._run(cls_prob, bbox_pred, im_info, features, grad_out, self.rois, self.pooled, self.grad_in, self.B, timer)
         return self.rois, self.pooled, self.grad_in
+
+    # ------------------------------------------------------------------ the same step, software-pipelined over batches
+    def _launch_proposal(self, cls_prob, bbox_pred, im_info, rois, stream):
+        check(self.lib.i2v_proposal_forward(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(self.anchors), self.B, self.A,
+                                            self.H, self.W, self.stride, self.pre, self.post, self.thr, _p(rois),
+                                            _p(self.counts), _p(self.ws_prop), self.ws_prop.numel(),
+                                            ctypes.c_void_p(stream.cuda_stream)), "proposal_forward")
+
+    def pipelined_step(self, cls_prob, bbox_pred, im_info, features, grad_out, next_rpn=None):
+        """One step whose proposal layer was (or is now) launched on a second stream, and which launches the NEXT
+        batch's proposal layer (`next_rpn = (cls_prob, bbox_pred, im_info)`) on that stream before its own RoIAlign
+        backward.  The proposal chain is latency-bound (one CTA per frame, 0.36 ms on 32 of 148 SMs); its CTAs slot in
+        between the waves of the backward kernel instead of holding the whole GPU.  Every step still runs all three
+        stages; only their placement in time changes.  Returns (rois, pooled, grad_in) of THIS step."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        if self._pending is None:                      # first step of a run: nothing was launched ahead
+            self._side.wait_stream(main)
+            self._launch_proposal(cls_prob, bbox_pred, im_info, self._rois_pp[0], self._side)
+            self._pending = (0, self._side.record_event())
+        cur, ready = self._pending
+        rois = self._rois_pp[cur]
+        main.wait_event(ready)
+        lib, s = self.lib, ctypes.c_void_p(main.cuda_stream)
+        check(lib.i2v_roi_align_forward(_p(features), _p(rois), _p(self.pooled), self.B, self.C, self.H, self.W, self.N,
+                                        self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO, _p(self.ws_roi),
+                                        self.ws_roi.numel(), s), "roi_align_forward")
+        if next_rpn is not None:
+            # the other roi buffer was last read by the step before this one, which the main stream has finished issuing;
+            # order the side stream after that work before it overwrites the buffer
+            fence = main.record_event()
+            self._side.wait_event(fence)
+            self._launch_proposal(next_rpn[0], next_rpn[1], next_rpn[2], self._rois_pp[cur ^ 1], self._side)
+            self._pending = (cur ^ 1, self._side.record_event())
+        else:
+            self._pending = None
+        check(lib.i2v_roi_align_backward(_p(grad_out), None, _p(rois), _p(self.grad_in), self.B, self.C, self.H, self.W,
+                                         self.N, self.P, self.P, self.scale, POOL_AVG, IMPL_AUTO, _p(self.ws_roi),
+                                         self.ws_roi.numel(), s), "roi_align_backward")
+        return rois, self.pooled, self.grad_in
 
     # ------------------------------------------------------------------ pinned host inputs and outputs
     def _host_buffers(self, cls_prob, bbox_pred, im_info, features, grad_out):

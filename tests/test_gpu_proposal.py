@@ -190,3 +190,26 @@ def test_host_pipeline_chunked_copy_equals_device_step():
         got = pipe.host_step(cls, reg, info, feat, grad, chunk_frames=chunk)
         for a, b in zip(got, want):
             assert torch.equal(a, b.cpu())
+
+
+def test_pipelined_step_equals_device_step():
+    """The software-pipelined step (proposal of the next batch on a second stream) returns what the plain step returns,
+    for a sequence of DIFFERENT batches."""
+    from i2vsgg_b200.pipeline import HostPipeline
+    frames, ch = 4, 32
+    dev = torch.device("cuda", 0)
+    pipe = HostPipeline(dev, frames, ch, 38, 63, 7, 1 / 16, 3000, 50, 0.7)
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn((frames, ch, 38, 63), generator=g).to(dev)
+    grad = torch.randn((frames * 50, ch, 7, 7), generator=g).to(dev)
+    batches = []
+    for k in range(3):
+        cls, reg = synth.rpn_outputs(80 + k, batch=frames)
+        batches.append(tuple(torch.from_numpy(a).to(dev) for a in (cls, reg, synth.im_info(frames))))
+    want = [[t.clone() for t in pipe.device_step(*b, feat, grad)] for b in batches]
+    for k, b in enumerate(batches):
+        nxt = batches[k + 1] if k + 1 < len(batches) else None
+        got = pipe.pipelined_step(*b, feat, grad, nxt)
+        torch.cuda.synchronize()
+        for a, w in zip(got, want[k]):
+            assert torch.equal(a, w)
