@@ -109,6 +109,8 @@ struct alignas(16) LatticeRoi {
     unsigned pad_;
 };
 
+constexpr size_t kRoiTabSlotBytes = 640;  // workspace bytes per RoI for the kernel-specific view of its tables
+
 // What the forward plane kernel needs of one RoI (lattices of up to 8 points per axis): byte offsets into the
 // [row][64 columns][16 channels] shared-memory planes and weights with validity (and the avg pool's 1/4) folded in.
 // A bilinear sample reads two horizontally adjacent cells; xa lists them even column first, xb odd column first.

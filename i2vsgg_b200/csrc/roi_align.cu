@@ -744,6 +744,12 @@ bool bwd_rows_ok(const float* grad_out, int batch, int C, int H, int W, int PH, 
 int launch_bwd_rows(const float* grad_out, const LatticeRoi* tab, void* rtab_space, const int* order, const int* starts,
                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 
+// roi_align_bwd_phase.cu: the phased backward (warp = lattice row, CTA barrier between feature-row phases)
+size_t bwd_phase_smem_bytes(int H, int W);
+bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
+int launch_bwd_phase(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
+                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
+
 struct LatticeWs {
     LatticeRoi* tab;
     PlaneTab* ptab;   // the plane tables share one allocation: the forward view or the backward view of a call
@@ -765,9 +771,11 @@ static LatticeWs carve_lattice_ws(void* ws, int batch, int num_rois, bool lists 
         w.counts = cv.take<int>((size_t)batch + 2);
         w.starts = cv.take<int>((size_t)batch + 2);
         w.order = cv.take<int>((size_t)num_rois);
-        w.ptab = cv.take<PlaneTab>((size_t)num_rois);
+        // one slot per RoI, shared by whichever per-kernel view of the tables a call builds (PlaneTab, BwdTab, or the
+        // RowTab / PhaseTab of roi_align_bwd_rows.cu / roi_align_bwd_phase.cu)
+        w.ptab = reinterpret_cast<PlaneTab*>(cv.take<unsigned char>((size_t)num_rois * kRoiTabSlotBytes));
         w.btab = reinterpret_cast<BwdTab*>(w.ptab);
-        static_assert(sizeof(BwdTab) <= sizeof(PlaneTab), "the backward table reuses the forward table's slot");
+        static_assert(sizeof(BwdTab) <= kRoiTabSlotBytes && sizeof(PlaneTab) <= kRoiTabSlotBytes, "table slot");
     }
     w.bytes = cv.used();
     return w;
@@ -867,7 +875,7 @@ static int roi_align_check(const char* who, const void* a, const void* b, const 
                            int& GH, int& GW) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0, "%s: negative size", who);
     I2V_REQUIRE(pool_mode >= I2V_POOL_NONE && pool_mode <= I2V_POOL_MAX, "%s: bad pool_mode %d", who, pool_mode);
-    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_ROWS, "%s: bad impl %d", who, impl);
+    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_PHASE, "%s: bad impl %d", who, impl);
     GH = pooled_h + (pool_mode != I2V_POOL_NONE);
     GW = pooled_w + (pool_mode != I2V_POOL_NONE);
     I2V_REQUIRE(pooled_h >= 1 && pooled_w >= 1 && GH >= 2 && GW >= 2 && GH <= kMaxLattice && GW <= kMaxLattice,
@@ -899,7 +907,7 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
                             pooled_h, pooled_w, pool_mode, impl, GH, GW));
     if (num_rois == 0 || channels == 0) return I2V_OK;
     bool can_plane = plane_forward_ok(out, batch, channels, height, width, pooled_h, pooled_w);
-    if ((impl == I2V_IMPL_PLANE || impl == I2V_IMPL_ROWS) && !can_plane) {
+    if (impl >= I2V_IMPL_PLANE && !can_plane) {
         set_error("roi_align_forward: the plane kernel needs a 7x7 output, C %% 16 == 0, a 16-byte aligned output and "
                   "16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
@@ -941,10 +949,19 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                      plane_backward_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     bool can_rows = zero_first && num_rois > 0 &&
                     bwd_rows_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
-    if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows)) {
+    bool can_phase = zero_first && num_rois > 0 &&
+                     bwd_phase_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows) ||
+        (impl == I2V_IMPL_PHASE && !can_phase)) {
         set_error("roi_align_backward: the plane kernels need a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
                   "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
+    }
+    if (can_phase && impl == I2V_IMPL_PHASE) {
+        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
+                                num_rois, pool_mode, stream);
     }
     // AUTO keeps the warp-per-RoI plane kernel: on config 2 it measures 2.28 ms against 2.38 ms for the row-owner kernel
     // (which trades the plane kernel's bank conflicts for a visit of every RoI by every warp; profiles/README.md)

@@ -1,0 +1,326 @@
+// RoIAlign / RoIAlignAvg backward, phased variant (roi_align_kernel.cu:94-143 behind the pool's backward,
+// modules/roi_align.py:18-29).
+//
+// One CTA per (frame, 16 channels) owns those 16 gradient planes in shared memory as [cell][16 channels] (64 bytes per
+// cell) and writes them to HBM once: no global atomics, no memset, deterministic.  The frame's RoIs stream through a TMA
+// ring (pooled-gradient tile [16][49] + the RoI's table) fed by a producer warp.
+//
+//   * lanes are (left / right cell of the bilinear pair) x (channel): the two cells a lattice point touches in one
+//     feature row are 128 contiguous bytes, so every read-modify-write of the planes is one conflict-free wavefront
+//     (the warp-per-channel-pair kernel in roi_align.cu pays 2.6 wavefronts per access for its scattered 8-byte cells);
+//   * consumer warp i owns lattice row i of the RoI in flight.  It forms the row's eight lattice gradients for its
+//     lane's channel straight from the tile (the 2x2 / stride-1 average pool's backward is a few adds over the pooled
+//     rows i-1 and i), scales them by the column weights, and then adds them into the row's upper feature row
+//     (phase A) and lower feature row (phase B).  Inside a phase the warps of one RoI touch distinct feature rows, so the
+//     only ordering needed is a CTA barrier between phases and between RoIs; the tile reads and the arithmetic of the
+//     next RoI sit between a warp's last store and its next barrier, which hides most of the wait;
+//   * lattice rows that share a start row (RoIs less than a cell high per bin) take turns by their position in the run;
+//     lattice columns whose cell pairs overlap are issued in batches that do not (`mode`, decided per RoI).
+#include "common.cuh"
+
+namespace i2v {
+
+struct alignas(16) PhaseTab {
+    // per half-warp h (= parity of the cells it owns) and lattice column j: the cell of the bilinear pair
+    // (start, start + 1) that has parity h, as a byte offset (cell * 64); its weight (validity and the avg pool's 1/4
+    // folded in); 1.0 when that cell is the same as column j-1's (the two contributions are then summed in registers)
+    int xoff[2][8];
+    float w[2][8];
+    float merge[2][8];
+    float4 yrow[8];       // {start row * W * 64 bytes (int bits), 1 - fy, fy, position in its run (int bits; -1: invalid)}
+    unsigned last[2];     // bit j: column j is the last of its run of equal cells, i.e. the one that is stored
+    int maxrun;           // longest run of lattice rows sharing a start row (0: nothing to scatter)
+    int pad_;
+};
+static_assert(sizeof(PhaseTab) == 336 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
+
+namespace {
+
+constexpr int kK = 16;
+constexpr int kGroups = 3;                              // groups of eight consumer warps that take the RoIs in turn
+constexpr int kConsumers = 8 * kGroups;
+constexpr int kThreads = (kConsumers + 1) * 32;
+constexpr int kStages = 19;
+constexpr int kTileBytes = kK * 49 * 4;                 // 3136
+constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 336
+constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3472
+constexpr int kRingBytes = kStages * kStageBytes;
+constexpr int kBarBytes = ((2 * kStages * 8 + 127) / 128) * 128;
+static_assert(kStageBytes % 16 == 0, "ring layout");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// named barriers: 1 = all consumer warps, 2 + g = "group g has finished its RoI" (group g arrives, the next group
+// waits), 2 + kGroups + g = the warps of group g between their two scatter phases
+__device__ __forceinline__ void bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- per-RoI tables
+__global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __restrict__ tab, PhaseTab* __restrict__ ptab,
+                                                         int num_rois, int G, int W, float wscale) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= num_rois) return;
+    const LatticeRoi& t = tab[n];
+    PhaseTab q;
+    const unsigned full = (1u << G) - 1u;
+    const unsigned vx = t.valid_x & full, vy = t.valid_y & full;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const bool oky = (vy >> p) & 1u;
+        q.yrow[p] = make_float4(__int_as_float(oky ? t.y.start[p] * W * 64 : 0), oky ? 1.f - t.y.frac[p] : 0.f,
+                                oky ? t.y.frac[p] : 0.f, __int_as_float(oky ? (int)((t.y_runpos >> (4 * p)) & 15u) : -1));
+    }
+    // Columns: starts are non-decreasing, so the cell of parity h under column j is non-decreasing in j too and equal
+    // cells are consecutive.  Each half-warp therefore sums a run of equal cells in registers and stores it once; the
+    // eight read-modify-writes of a feature row never meet in a cell, whatever the RoI's width.
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int prev = -1;
+        unsigned last = 0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const bool okx = (vx >> p) & 1u;
+            const int st = t.x.start[p];
+            const int cell = st + ((st & 1) ^ h);
+            const bool left = (st & 1) == h;                      // this half-warp owns the pair's left cell
+            q.xoff[h][p] = okx ? cell * 64 : 0;
+            q.w[h][p] = okx ? (left ? 1.f - t.x.frac[p] : t.x.frac[p]) * wscale : 0.f;
+            const bool mrg = okx && cell == prev;
+            q.merge[h][p] = mrg ? 1.f : 0.f;
+            if (mrg) last &= ~(1u << (p - 1));
+            if (okx) {
+                last |= 1u << p;
+                prev = cell;
+            }
+        }
+        q.last[h] = last;
+    }
+    const bool any = t.batch >= 0 && vx != 0u && vy != 0u;
+    q.maxrun = any ? (int)t.y_maxrun : 0;
+    q.pad_ = 0;
+    ptab[n] = q;
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+// One feature row of one lattice row: the lane's eight cells += val[j] * wy, stored where `last` says the column closes
+// its run of equal cells (val[] already holds the run's sum there).  All eight are independent.
+template <int G>
+__device__ __forceinline__ void scatter_row(unsigned char* rowp, const int (&xo)[8], const float (&val)[8], float wy,
+                                            unsigned last) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < G; ++j) o[j] = *reinterpret_cast<const float*>(rowp + xo[j]);
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+        if ((last >> j) & 1u) *reinterpret_cast<float*>(rowp + xo[j]) = fmaf(val[j], wy, o[j]);
+}
+
+template <int POOL, int WT>
+__global__ void __launch_bounds__(kThreads, 1)
+    lattice_bwd_phase_kernel(const float* __restrict__ grad_out, const PhaseTab* __restrict__ ptab,
+                             const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ grad_in,
+                             int C, int H, int Wrt) {
+    constexpr int P = 7;
+    constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = WT ? WT : Wrt;
+    const int HW = H * W;
+    unsigned char* ring = smem;                                                    // [kStages][tile | table]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingBytes);               // [kStages]
+    uint64_t* empty = full + kStages;
+    float* planes = reinterpret_cast<float*>(smem + kRingBytes + kBarBytes);       // [H * W][16]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctiles = C / kK;
+    const int ct = blockIdx.x % ctiles;
+    const int b = blockIdx.x / ctiles;
+    const int list_lo = __ldg(starts + b), list_hi = __ldg(starts + b + 1);
+    const int count = list_hi - list_lo;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 8);        // the eight warps of the group that owns the stage's RoI
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        float4* z = reinterpret_cast<float4*>(planes);
+        for (int i = tid; i < HW * kK / 4; i += kThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (warp == kConsumers) {
+        // ---- producer: lane j feeds ring stage j, so the barrier handshake of one stage never holds up another ----
+        if (lane < kStages) {
+            unsigned char* dst = ring + lane * kStageBytes;
+            unsigned round = 0;
+            for (int k = lane; k < count; k += kStages, ++round) {
+                const int n = __ldg(order + list_lo + k);
+                if (round > 0) mbar_wait(empty + lane, (round - 1) & 1);
+                mbar_expect_tx(full + lane, kStageBytes);
+                bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kK) * 49, kTileBytes, full + lane);
+                bulk_load(dst + kTileBytes, ptab + n, kTabBytes, full + lane);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: group = RoIs k = g (mod kGroups), warp in group = lattice row, lane = (dx, channel).  While one
+    // group scatters its RoI the others fetch and reduce theirs; the scatters themselves stay in list order (the done
+    // barrier of the previous group), so the result does not depend on timing ----
+    const int grp = warp >> 3, row = warp & 7;
+    const int hx = lane >> 4, c = lane & 15;     // hx: parity of the cells this half-warp owns
+    const int row_bytes = W * 64;
+    unsigned char* lane_planes = reinterpret_cast<unsigned char*>(planes) + c * 4;
+    const int ra_off = (c * 49 + max(row - 1, 0) * P) * 4, rb_off = (c * 49 + min(row, P - 1) * P) * 4;
+    const float ma = (POOL == I2V_POOL_NONE) ? 0.f : (row >= 1 ? 1.f : 0.f);
+    const float mb = row < P ? 1.f : 0.f;
+    const int bar_prev = 2 + (grp + kGroups - 1) % kGroups, bar_mine = 2 + grp, bar_intra = 2 + kGroups + grp;
+
+    int s = grp % kStages;
+    unsigned round = 0;
+    for (int k = grp; k < count; k += kGroups) {
+        // ---- fetch + reduce: the lane's eight weighted lattice gradients of lattice row `row` ----
+        mbar_wait(full + s, round & 1);
+        const unsigned char* stage = ring + s * kStageBytes;
+        const PhaseTab* t = reinterpret_cast<const PhaseTab*>(stage + kTileBytes);
+        const int maxrun = t->maxrun;
+        const unsigned last = t->last[hx];
+        const float4 yr = t->yrow[row];
+        const int4 o0 = *reinterpret_cast<const int4*>(t->xoff[hx]), o1 = *reinterpret_cast<const int4*>(t->xoff[hx] + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
+        const float4 m0 = *reinterpret_cast<const float4*>(t->merge[hx]), m1 = *reinterpret_cast<const float4*>(t->merge[hx] + 4);
+        const float* ra = reinterpret_cast<const float*>(stage + ra_off);
+        const float* rb = reinterpret_cast<const float*>(stage + rb_off);
+        const int runpos = (row < G) ? __float_as_int(yr.w) : -1;
+        const float wy0 = yr.y, wy1 = yr.z;
+        unsigned char* rowp = lane_planes + __float_as_int(yr.x);
+        const int xo[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        const float wl[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float mf[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float val[8];
+        if (POOL == I2V_POOL_NONE) {
+            // lattice == pooled grid: lattice row i is pooled row i
+#pragma unroll
+            for (int j = 0; j < P; ++j) val[j] = rb[j] * mb * wl[j];
+            val[7] = 0.f;
+        } else {
+            // lattice row i collects the pooled rows i-1 and i, lattice column j the pooled columns j-1 and j
+            float sj[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) sj[j] = ra[j] * ma + rb[j] * mb;
+            val[0] = sj[0] * wl[0];
+#pragma unroll
+            for (int j = 1; j < P; ++j) val[j] = (sj[j - 1] + sj[j]) * wl[j];
+            val[7] = sj[P - 1] * wl[7];
+        }
+        // columns that fall into the cell of the column before them carry that column's sum along
+#pragma unroll
+        for (int j = 1; j < G; ++j) val[j] = fmaf(mf[j], val[j - 1], val[j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);      // the stage's bytes are in registers now
+        s += kGroups;
+        if (s >= kStages) {
+            s -= kStages;
+            ++round;
+        }
+        // ---- scatter, after RoI k-1 ----
+        if (k > 0) bar_sync(bar_prev, 512);
+        for (int r = 0; r < maxrun; ++r) {          // maxrun == 0: nothing to scatter (uniform over the CTA)
+            const bool mine = runpos == r;
+            if (r > 0) bar_sync(bar_intra, 256);
+            if (mine) scatter_row<G>(rowp, xo, val, wy0, last);
+            bar_sync(bar_intra, 256);
+            if (mine) scatter_row<G>(rowp + row_bytes, xo, val, wy1, last);
+        }
+        if (k + 1 < count) {
+            __threadfence_block();
+            bar_arrive(bar_mine, 512);
+        }
+    }
+
+    // ---- write-out: [cell][16] in shared memory -> [16][cell] in HBM.  A lane reads four channels of one cell (16 bytes,
+    // the warp 512 contiguous bytes) and stores them to four planes; eight lanes cover one 32-byte sector of a plane ----
+    bar_sync(1, kConsumers * 32);
+    {
+        const int q = lane & 3;
+        float* dst = grad_in + ((size_t)b * C + (size_t)ct * kK + (size_t)q * 4) * HW;
+        const float4* src = reinterpret_cast<const float4*>(planes);
+        for (int cell = warp * 8 + (lane >> 2); cell < HW; cell += kConsumers * 8) {
+            const float4 v = src[cell * 4 + q];
+            dst[cell] = v.x;
+            dst[(size_t)HW + cell] = v.y;
+            dst[(size_t)2 * HW + cell] = v.z;
+            dst[(size_t)3 * HW + cell] = v.w;
+        }
+    }
+}
+
+}  // namespace
+
+size_t bwd_phase_smem_bytes(int H, int W) { return (size_t)kRingBytes + kBarBytes + (size_t)H * W * kK * sizeof(float); }
+
+bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode) {
+    return batch > 0 && PH == 7 && PW == 7 && pool_mode != I2V_POOL_MAX && C % kK == 0 && H >= 2 && W >= 2 &&
+           bwd_phase_smem_bytes(H, W) <= (size_t)kMaxSmemPerCta && ((uintptr_t)grad_out & 15) == 0;
+}
+
+template <int POOL, int WT>
+static int launch_phase(const float* grad_out, const PhaseTab* ptab, const int* order, const int* starts, float* grad_in,
+                        int batch, int C, int H, int W, cudaStream_t stream) {
+    auto kern = lattice_bwd_phase_kernel<POOL, WT>;
+    const size_t smem = bwd_phase_smem_bytes(H, W);
+    I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)(batch * (C / kK))), kThreads, smem, stream>>>(grad_out, ptab, order, starts, grad_in, C, H, W);
+    return check_launch("lattice_bwd_phase_kernel");
+}
+
+// `tab` holds the LatticeRoi tables of this call; `tab_space` is the workspace's per-RoI table slot (kRoiTabSlotBytes each).
+int launch_bwd_phase(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
+                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream) {
+    PhaseTab* ptab = static_cast<PhaseTab*>(tab_space);
+    const int G = pool_mode == I2V_POOL_NONE ? 7 : 8;
+    phase_prep_kernel<<<ceil_div(num_rois, 128), 128, 0, stream>>>(tab, ptab, num_rois, G, W,
+                                                                    pool_mode == I2V_POOL_AVG ? 0.25f : 1.f);
+    I2V_TRY(check_launch("phase_prep_kernel"));
+    if (pool_mode == I2V_POOL_AVG) {
+        if (W == 63) return launch_phase<I2V_POOL_AVG, 63>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
+        return launch_phase<I2V_POOL_AVG, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
+    }
+    return launch_phase<I2V_POOL_NONE, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
+}
+
+}  // namespace i2v

@@ -31,7 +31,7 @@ struct alignas(16) RowTab {
     unsigned char rowrange[48];// per feature row: first lattice row contributing to it | (number of them) << 4, 0xFF: none
     float rc[48][2];           // the coefficients of the first two of them
 };
-static_assert(sizeof(RowTab) == 608, "RowTab layout");
+static_assert(sizeof(RowTab) == 608 && sizeof(RowTab) <= kRoiTabSlotBytes, "RowTab layout");
 
 namespace {
 
@@ -392,7 +392,7 @@ bool bwd_rows_ok(const float* grad_out, int batch, int C, int H, int W, int PH, 
            H <= kMaxRows && bwd_rows_smem_bytes(H, W) <= (size_t)kMaxSmemPerCta && ((uintptr_t)grad_out & 15) == 0;
 }
 
-// `tab` holds the LatticeRoi tables of this call; `rtab_space` is the (>= 224 bytes per RoI) slot for the RowTab views.
+// `tab` holds the LatticeRoi tables of this call; `rtab_space` is the workspace's per-RoI table slot (kRoiTabSlotBytes each).
 int launch_bwd_rows(const float* grad_out, const LatticeRoi* tab, void* rtab_space, const int* order, const int* starts,
                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream) {
     RowTab* rtab = static_cast<RowTab*>(rtab_space);

@@ -78,6 +78,8 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
 #define I2V_IMPL_PLANE 2   /* frame plane staged in shared memory; I2V_ERR_UNSUPPORTED if it cannot    */
 #define I2V_IMPL_ROWS 3    /* backward only: plane-resident, warps own feature rows (bank-conflict free by
                               construction; forward treats it like I2V_IMPL_PLANE)                                 */
+#define I2V_IMPL_PHASE 4   /* backward only: plane-resident, warp = lattice row, lanes = (cell of the bilinear pair,
+                              channel); conflict-free, CTA barrier between feature-row phases (forward: like PLANE)    */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.

@@ -95,10 +95,10 @@ def test_roi_align_empty(ops):
 
 
 @pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "auto"])
+@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "phase", "auto"])
 @pytest.mark.parametrize("case", CASES)
 def test_roi_align_backward(ops, orc, case, impl, pool):
-    if impl in ("plane", "rows") and pool == "max":
+    if impl in ("plane", "rows", "phase") and pool == "max":
         pytest.skip("the max pool's arg-max routing needs the features: gather kernel only")
     B, C, H, W, N = case
     feat = synth.feature_map(100 + B, B, C, H, W)
@@ -126,7 +126,7 @@ def test_roi_align_backward_small_and_repeated_cells(ops, orc):
     for pool in ("avg", "none"):
         want = orc.roi_align_pooled_backward(g, None if pool != "max" else None, rois, 7, 7, SCALE, pool) \
             if False else orc.roi_align_pooled_backward(g, np.zeros(feat_shape, np.float32), rois, 7, 7, SCALE, pool)
-        for impl in ("plane", "rows"):
+        for impl in ("plane", "rows", "phase"):
             got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
             close(got, want)
             again = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
@@ -363,3 +363,7 @@ def test_roi_align_properties_at_config2_size(ops, orc):
     rows = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "rows")
     assert float((rows - gin).abs().max()) <= 1e-5 * float(gin.abs().max())
     assert torch.equal(rows, ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "rows"))
+    del rows, again
+    phase = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase")
+    assert float((phase - gin).abs().max()) <= 1e-5 * float(gin.abs().max())
+    assert torch.equal(phase, ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase"))
