@@ -28,9 +28,8 @@ struct alignas(16) PhaseTab {
     float w[2][8];
     float merge[2][8];
     float4 yrow[8];       // {start row * W * 64 bytes (int bits), 1 - fy, fy, position in its run (int bits; -1: invalid)}
-    unsigned last[2];     // bit j: column j is the last of its run of equal cells, i.e. the one that is stored
     int maxrun;           // longest run of lattice rows sharing a start row (0: nothing to scatter)
-    int pad_;
+    int pad_[3];
 };
 static_assert(sizeof(PhaseTab) == 336 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
 
@@ -102,48 +101,57 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
                                 oky ? t.y.frac[p] : 0.f, __int_as_float(oky ? (int)((t.y_runpos >> (4 * p)) & 15u) : -1));
     }
     // Columns: starts are non-decreasing, so the cell of parity h under column j is non-decreasing in j too and equal
-    // cells are consecutive.  Each half-warp therefore sums a run of equal cells in registers and stores it once; the
-    // eight read-modify-writes of a feature row never meet in a cell, whatever the RoI's width.
+    // cells are consecutive.  Each lane sums a run of equal cells in registers (merge) and stores every column in order:
+    // the last store of a run carries the whole sum and overwrites the partial ones before it (same thread, same
+    // address), so the eight read-modify-writes of a feature row never lose an update, whatever the RoI's width.
+    // Columns off the map (a prefix or a suffix) join the nearest valid column's run with weight zero.
+    int fv = -1, lv = -1;
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        if ((vx >> p) & 1u) {
+            if (fv < 0) fv = p;
+            lv = p;
+        }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         int prev = -1;
-        unsigned last = 0;
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             const bool okx = (vx >> p) & 1u;
-            const int st = t.x.start[p];
+            const int q_ = okx ? p : (fv < 0 ? 0 : (p < fv ? fv : lv));
+            const int st = t.x.start[q_];
             const int cell = st + ((st & 1) ^ h);
             const bool left = (st & 1) == h;                      // this half-warp owns the pair's left cell
-            q.xoff[h][p] = okx ? cell * 64 : 0;
+            q.xoff[h][p] = cell * 64;
             q.w[h][p] = okx ? (left ? 1.f - t.x.frac[p] : t.x.frac[p]) * wscale : 0.f;
-            const bool mrg = okx && cell == prev;
-            q.merge[h][p] = mrg ? 1.f : 0.f;
-            if (mrg) last &= ~(1u << (p - 1));
-            if (okx) {
-                last |= 1u << p;
-                prev = cell;
-            }
+            q.merge[h][p] = (p > 0 && cell == prev) ? 1.f : 0.f;
+            prev = cell;
         }
-        q.last[h] = last;
     }
     const bool any = t.batch >= 0 && vx != 0u && vy != 0u;
     q.maxrun = any ? (int)t.y_maxrun : 0;
-    q.pad_ = 0;
+    q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
     ptab[n] = q;
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// One feature row of one lattice row: the lane's eight cells += val[j] * wy, stored where `last` says the column closes
-// its run of equal cells (val[] already holds the run's sum there).  All eight are independent.
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// One feature row of one lattice row: the lane's eight cells += val[j] * wy.  All eight loads are issued before the
+// first store; columns that share a cell hold running sums, so storing in column order leaves the complete one.
 template <int G>
-__device__ __forceinline__ void scatter_row(unsigned char* rowp, const int (&xo)[8], const float (&val)[8], float wy,
-                                            unsigned last) {
+__device__ __forceinline__ void scatter_row(const unsigned (&addr)[8], unsigned row_off, const float (&val)[8], float wy) {
     float o[8];
 #pragma unroll
-    for (int j = 0; j < G; ++j) o[j] = *reinterpret_cast<const float*>(rowp + xo[j]);
+    for (int j = 0; j < G; ++j) o[j] = lds_f32(addr[j] + row_off);
 #pragma unroll
-    for (int j = 0; j < G; ++j)
-        if ((last >> j) & 1u) *reinterpret_cast<float*>(rowp + xo[j]) = fmaf(val[j], wy, o[j]);
+    for (int j = 0; j < G; ++j) sts_f32(addr[j] + row_off, fmaf(val[j], wy, o[j]));
 }
 
 template <int POOL, int WT>
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int grp = warp >> 3, row = warp & 7;
     const int hx = lane >> 4, c = lane & 15;     // hx: parity of the cells this half-warp owns
     const int row_bytes = W * 64;
-    unsigned char* lane_planes = reinterpret_cast<unsigned char*>(planes) + c * 4;
+    const unsigned lane_planes = smem_u32(planes) + c * 4;
     const int ra_off = (c * 49 + max(row - 1, 0) * P) * 4, rb_off = (c * 49 + min(row, P - 1) * P) * 4;
     const float ma = (POOL == I2V_POOL_NONE) ? 0.f : (row >= 1 ? 1.f : 0.f);
     const float mb = row < P ? 1.f : 0.f;
@@ -218,7 +226,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         const unsigned char* stage = ring + s * kStageBytes;
         const PhaseTab* t = reinterpret_cast<const PhaseTab*>(stage + kTileBytes);
         const int maxrun = t->maxrun;
-        const unsigned last = t->last[hx];
         const float4 yr = t->yrow[row];
         const int4 o0 = *reinterpret_cast<const int4*>(t->xoff[hx]), o1 = *reinterpret_cast<const int4*>(t->xoff[hx] + 4);
         const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
@@ -227,8 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float* rb = reinterpret_cast<const float*>(stage + rb_off);
         const int runpos = (row < G) ? __float_as_int(yr.w) : -1;
         const float wy0 = yr.y, wy1 = yr.z;
-        unsigned char* rowp = lane_planes + __float_as_int(yr.x);
-        const int xo[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        const unsigned rowa = lane_planes + (unsigned)__float_as_int(yr.x);
+        const unsigned addr[8] = {rowa + o0.x, rowa + o0.y, rowa + o0.z, rowa + o0.w,
+                                  rowa + o1.x, rowa + o1.y, rowa + o1.z, rowa + o1.w};
         const float wl[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const float mf[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
         float val[8];
@@ -262,14 +270,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int r = 0; r < maxrun; ++r) {          // maxrun == 0: nothing to scatter (uniform over the CTA)
             const bool mine = runpos == r;
             if (r > 0) bar_sync(bar_intra, 256);
-            if (mine) scatter_row<G>(rowp, xo, val, wy0, last);
+            if (mine) scatter_row<G>(addr, 0u, val, wy0);
             bar_sync(bar_intra, 256);
-            if (mine) scatter_row<G>(rowp + row_bytes, xo, val, wy1, last);
+            if (mine) scatter_row<G>(addr, (unsigned)row_bytes, val, wy1);
         }
-        if (k + 1 < count) {
-            __threadfence_block();
-            bar_arrive(bar_mine, 512);
-        }
+        // bar.arrive orders this thread's earlier shared-memory accesses before the barrier's completion (PTX ISA,
+        // barrier.cta: "prior memory accesses requested by this thread are performed relative to all participants")
+        if (k + 1 < count) bar_arrive(bar_mine, 512);
     }
 
     // ---- write-out: [cell][16] in shared memory -> [16][cell] in HBM.  A lane reads four channels of one cell (16 bytes,
