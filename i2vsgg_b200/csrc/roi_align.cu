@@ -957,14 +957,14 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                   "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
     }
-    if (can_phase && impl == I2V_IMPL_PHASE) {
+    // AUTO takes the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
+    // 2.35 ms for the row-owner kernel (profiles/README.md); the other two stay selectable and serve as cross-checks
+    if (can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO)) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
         return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
                                 num_rois, pool_mode, stream);
     }
-    // AUTO keeps the warp-per-RoI plane kernel: on config 2 it measures 2.28 ms against 2.38 ms for the row-owner kernel
-    // (which trades the plane kernel's bank conflicts for a visit of every RoI by every warp; profiles/README.md)
     if (can_rows && (impl == I2V_IMPL_ROWS || (impl == I2V_IMPL_AUTO && !can_plane))) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));

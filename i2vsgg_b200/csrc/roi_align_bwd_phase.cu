@@ -29,7 +29,8 @@ struct alignas(16) PhaseTab {
     float merge[2][8];
     float4 yrow[8];       // {start row * W * 64 bytes (int bits), 1 - fy, fy, position in its run (int bits; -1: invalid)}
     int maxrun;           // longest run of lattice rows sharing a start row (0: nothing to scatter)
-    int pad_[3];
+    int rows_apart;       // 1: consecutive valid lattice rows start at least two feature rows apart (all 16 rows distinct)
+    int pad_[2];
 };
 static_assert(sizeof(PhaseTab) == 336 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
 
@@ -130,7 +131,17 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
     }
     const bool any = t.batch >= 0 && vx != 0u && vy != 0u;
     q.maxrun = any ? (int)t.y_maxrun : 0;
-    q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
+    {
+        int prev = -100, apart = 1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if ((vy >> p) & 1u) {
+                if (t.y.start[p] - prev < 2) apart = 0;
+                prev = t.y.start[p];
+            }
+        q.rows_apart = apart;
+    }
+    q.pad_[0] = q.pad_[1] = 0;
     ptab[n] = q;
 }
 
@@ -191,16 +202,27 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncthreads();
 
     if (warp == kConsumers) {
-        // ---- producer: lane j feeds ring stage j, so the barrier handshake of one stage never holds up another ----
-        if (lane < kStages) {
-            unsigned char* dst = ring + lane * kStageBytes;
-            unsigned round = 0;
-            for (int k = lane; k < count; k += kStages, ++round) {
-                const int n = __ldg(order + list_lo + k);
-                if (round > 0) mbar_wait(empty + lane, (round - 1) & 1);
-                mbar_expect_tx(full + lane, kStageBytes);
-                bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kK) * 49, kTileBytes, full + lane);
-                bulk_load(dst + kTileBytes, ptab + n, kTabBytes, full + lane);
+        // ---- producer: the warp reads the frame's RoI list 32 entries at a time; lane 0 walks the ring in order (the
+        // consumers release the stages in list order too) and issues the two bulk copies of each RoI ----
+        int st = 0;
+        unsigned round = 0;
+        for (int base = 0; base < count; base += 32) {
+            const int mine = (base + lane < count) ? __ldg(order + list_lo + base + lane) : 0;
+            const int lim = min(32, count - base);
+            for (int i = 0; i < lim; ++i) {
+                const int n = __shfl_sync(0xffffffffu, mine, i);
+                if (lane == 0) {
+                    if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                    unsigned char* dst = ring + st * kStageBytes;
+                    mbar_expect_tx(full + st, kStageBytes);
+                    bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kK) * 49, kTileBytes, full + st);
+                    bulk_load(dst + kTileBytes, ptab + n, kTabBytes, full + st);
+                }
+                if (++st == kStages) {
+                    st = 0;
+                    ++round;
+                }
+                __syncwarp();
             }
         }
         return;
@@ -225,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(full + s, round & 1);
         const unsigned char* stage = ring + s * kStageBytes;
         const PhaseTab* t = reinterpret_cast<const PhaseTab*>(stage + kTileBytes);
-        const int maxrun = t->maxrun;
+        const int2 hd = *reinterpret_cast<const int2*>(&t->maxrun);
+        const int maxrun = hd.x;
         const float4 yr = t->yrow[row];
         const int4 o0 = *reinterpret_cast<const int4*>(t->xoff[hx]), o1 = *reinterpret_cast<const int4*>(t->xoff[hx] + 4);
         const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
@@ -267,6 +290,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         // ---- scatter, after RoI k-1 ----
         if (k > 0) bar_sync(bar_prev, 512);
+        if (hd.y) {
+            // tall RoI: the sixteen feature rows under the eight lattice rows are all different, one phase will do
+            if (runpos == 0) {
+                float oa[8], ob[8];
+#pragma unroll
+                for (int j = 0; j < G; ++j) oa[j] = lds_f32(addr[j]);
+#pragma unroll
+                for (int j = 0; j < G; ++j) ob[j] = lds_f32(addr[j] + (unsigned)row_bytes);
+#pragma unroll
+                for (int j = 0; j < G; ++j) sts_f32(addr[j], fmaf(val[j], wy0, oa[j]));
+#pragma unroll
+                for (int j = 0; j < G; ++j) sts_f32(addr[j] + (unsigned)row_bytes, fmaf(val[j], wy1, ob[j]));
+            }
+        } else
         for (int r = 0; r < maxrun; ++r) {          // maxrun == 0: nothing to scatter (uniform over the CTA)
             const bool mine = runpos == r;
             if (r > 0) bar_sync(bar_intra, 256);

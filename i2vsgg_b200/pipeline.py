@@ -64,8 +64,8 @@ class HostPipeline:
                                    dtype=torch.uint8, device=device)
         self.ws_roi = torch.empty(self.lib.i2v_roi_align_workspace_bytes(frames, self.N), dtype=torch.uint8,
                                   device=device)
-        # kernels per step: decode, sort, nms | prep, bucket, forward | prep, (bucket,) backward (memsets not counted)
-        self.launches_per_step = 9
+        # kernels per step: decode, sort, nms | prep, bucket, forward | prep, bucket, phase tables, backward (memsets not counted)
+        self.launches_per_step = 10
         self._host = None
 
     # ------------------------------------------------------------------ device-resident inputs

@@ -22,6 +22,15 @@ def main():
     rois = ops.proposal_forward(cu(cls), cu(reg), cu(synth.im_info(B)), cu(synth.BASE_ANCHORS), 16, 12000, 300,
                                 0.7).reshape(-1, 5)
     N = rois.size(0)
+    if os.environ.get("ROI_STATS"):
+        r = rois.cpu().numpy()
+        bw = ((r[:, 3] - r[:, 1]) / 16 + 1) / 7
+        bh = ((r[:, 4] - r[:, 2]) / 16 + 1) / 7
+        qs = [0.05, 0.25, 0.5, 0.75, 0.95]
+        print(json.dumps({"rois": int(N), "bin_w_cells_quantiles": np.quantile(bw, qs).round(2).tolist(),
+                          "bin_h_cells_quantiles": np.quantile(bh, qs).round(2).tolist(),
+                          "frac_bin_h_ge2": float((bh >= 2).mean()), "frac_bin_h_lt1": float((bh < 1).mean()),
+                          "frac_bin_w_ge2": float((bw >= 2).mean()), "frac_bin_w_lt1": float((bw < 1).mean())}))
     g = torch.randn((N, C, 7, 7), device="cuda")
     nbytes = N * C * 49 * 4 + B * C * H * W * 4 + N * 20
     ref = None
