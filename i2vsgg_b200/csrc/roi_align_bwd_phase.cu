@@ -5,17 +5,25 @@
 // cell) and writes them to HBM once: no global atomics, no memset, deterministic.  The frame's RoIs stream through a TMA
 // ring (pooled-gradient tile [16][49] + the RoI's table) fed by a producer warp.
 //
-//   * lanes are (left / right cell of the bilinear pair) x (channel): the two cells a lattice point touches in one
-//     feature row are 128 contiguous bytes, so every read-modify-write of the planes is one conflict-free wavefront
-//     (the warp-per-channel-pair kernel in roi_align.cu pays 2.6 wavefronts per access for its scattered 8-byte cells);
-//   * consumer warp i owns lattice row i of the RoI in flight.  It forms the row's eight lattice gradients for its
+//   * lanes are (parity of the cell's column) x (channel): the two cells a lattice point touches in one feature row are
+//     128 contiguous bytes, one owned by each half-warp, so every read-modify-write of the planes is one conflict-free
+//     wavefront (the warp-per-channel-pair kernel in roi_align.cu pays 2.6 wavefronts per access for its scattered
+//     8-byte cells).  Because a lane always owns the cells of one parity, two lattice columns that fall into the same
+//     cell (RoIs narrower than two cells per bin) meet in the SAME lane: the lane carries a running sum along such a
+//     run and stores every column in order, the last store holding the whole sum.  The eight read-modify-writes of a
+//     feature row are therefore always independent -- all loads first, then all stores -- whatever the RoI's width;
+//   * a consumer warp owns one lattice row of the RoI in flight.  It forms the row's eight lattice gradients for its
 //     lane's channel straight from the tile (the 2x2 / stride-1 average pool's backward is a few adds over the pooled
-//     rows i-1 and i), scales them by the column weights, and then adds them into the row's upper feature row
-//     (phase A) and lower feature row (phase B).  Inside a phase the warps of one RoI touch distinct feature rows, so the
-//     only ordering needed is a CTA barrier between phases and between RoIs; the tile reads and the arithmetic of the
-//     next RoI sit between a warp's last store and its next barrier, which hides most of the wait;
+//     rows i-1 and i), scales them by the column weights, and adds them into the row's upper feature row (phase A) and
+//     lower feature row (phase B).  Inside a phase the warps of one RoI touch distinct feature rows; a barrier of the
+//     eight warps separates the phases (not needed when the RoI is tall enough for all sixteen rows to differ);
 //   * lattice rows that share a start row (RoIs less than a cell high per bin) take turns by their position in the run;
-//     lattice columns whose cell pairs overlap are issued in batches that do not (`mode`, decided per RoI).
+//   * three groups of eight warps take the RoIs in turn.  While one group scatters, the others fetch and reduce theirs;
+//     a named barrier (the finishing group arrives, the next group waits) keeps the scatters in list order, so the
+//     result is bit-reproducible.
+//
+// Measured on config 2 (profiles/README.md): 1.59 ms against 2.28 ms; what binds it is the serial chain of scatter
+// phases (about 760 cycles per RoI against 256 cycles of shared-memory wavefronts) and, right behind it, the ring feed.
 #include "common.cuh"
 
 namespace i2v {
