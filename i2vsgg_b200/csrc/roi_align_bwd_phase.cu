@@ -30,17 +30,17 @@ namespace i2v {
 
 struct alignas(16) PhaseTab {
     // per half-warp h (= parity of the cells it owns) and lattice column j: the cell of the bilinear pair
-    // (start, start + 1) that has parity h, as a byte offset (cell * 64); its weight (validity and the avg pool's 1/4
-    // folded in); 1.0 when that cell is the same as column j-1's (the two contributions are then summed in registers)
-    int xoff[2][8];
+    // (start, start + 1) that has parity h (a 16-bit cell index), and its weight (validity and the avg pool's 1/4 folded in)
+    unsigned short xcell[2][8];
     float w[2][8];
-    float merge[2][8];
     float4 yrow[8];       // {start row * W * 64 bytes (int bits), 1 - fy, fy, position in its run (int bits; -1: invalid)}
     int maxrun;           // longest run of lattice rows sharing a start row (0: nothing to scatter)
     int rows_apart;       // 1: consecutive valid lattice rows start at least two feature rows apart (all 16 rows distinct)
-    int pad_[2];
+    unsigned merge;       // bit 8 h + j: for half-warp h, column j falls into the same cell as column j-1 (the two
+                          // contributions are then summed in registers)
+    int pad_;
 };
-static_assert(sizeof(PhaseTab) == 336 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
+static_assert(sizeof(PhaseTab) == 240 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
 
 namespace {
 
@@ -48,10 +48,10 @@ constexpr int kK = 16;
 constexpr int kGroups = 3;                              // groups of eight consumer warps that take the RoIs in turn
 constexpr int kConsumers = 8 * kGroups;
 constexpr int kThreads = (kConsumers + 1) * 32;
-constexpr int kStages = 19;
+constexpr int kStages = 20;
 constexpr int kTileBytes = kK * 49 * 4;                 // 3136
-constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 336
-constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3472
+constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 240
+constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3376
 constexpr int kRingBytes = kStages * kStageBytes;
 constexpr int kBarBytes = ((2 * kStages * 8 + 127) / 128) * 128;
 static_assert(kStageBytes % 16 == 0, "ring layout");
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
             if (fv < 0) fv = p;
             lv = p;
         }
+    unsigned mergebits = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         int prev = -1;
@@ -131,9 +132,9 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
             const int st = t.x.start[q_];
             const int cell = st + ((st & 1) ^ h);
             const bool left = (st & 1) == h;                      // this half-warp owns the pair's left cell
-            q.xoff[h][p] = cell * 64;
+            q.xcell[h][p] = (unsigned short)cell;
             q.w[h][p] = okx ? (left ? 1.f - t.x.frac[p] : t.x.frac[p]) * wscale : 0.f;
-            q.merge[h][p] = (p > 0 && cell == prev) ? 1.f : 0.f;
+            if (p > 0 && cell == prev) mergebits |= 1u << (8 * h + p);
             prev = cell;
         }
     }
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
             }
         q.rows_apart = apart;
     }
-    q.pad_[0] = q.pad_[1] = 0;
+    q.merge = mergebits;
+    q.pad_ = 0;
     ptab[n] = q;
 }
 
@@ -255,21 +257,22 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(full + s, round & 1);
         const unsigned char* stage = ring + s * kStageBytes;
         const PhaseTab* t = reinterpret_cast<const PhaseTab*>(stage + kTileBytes);
-        const int2 hd = *reinterpret_cast<const int2*>(&t->maxrun);
+        const int4 hd = *reinterpret_cast<const int4*>(&t->maxrun);    // {maxrun, rows_apart, merge bits, -}
         const int maxrun = hd.x;
         const float4 yr = t->yrow[row];
-        const int4 o0 = *reinterpret_cast<const int4*>(t->xoff[hx]), o1 = *reinterpret_cast<const int4*>(t->xoff[hx] + 4);
+        const uint4 xc = *reinterpret_cast<const uint4*>(t->xcell[hx]);         // eight 16-bit cell indices
         const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
-        const float4 m0 = *reinterpret_cast<const float4*>(t->merge[hx]), m1 = *reinterpret_cast<const float4*>(t->merge[hx] + 4);
         const float* ra = reinterpret_cast<const float*>(stage + ra_off);
         const float* rb = reinterpret_cast<const float*>(stage + rb_off);
         const int runpos = (row < G) ? __float_as_int(yr.w) : -1;
         const float wy0 = yr.y, wy1 = yr.z;
         const unsigned rowa = lane_planes + (unsigned)__float_as_int(yr.x);
-        const unsigned addr[8] = {rowa + o0.x, rowa + o0.y, rowa + o0.z, rowa + o0.w,
-                                  rowa + o1.x, rowa + o1.y, rowa + o1.z, rowa + o1.w};
+        const unsigned addr[8] = {rowa + (xc.x & 0xffffu) * 64u, rowa + (xc.x >> 16) * 64u,
+                                  rowa + (xc.y & 0xffffu) * 64u, rowa + (xc.y >> 16) * 64u,
+                                  rowa + (xc.z & 0xffffu) * 64u, rowa + (xc.z >> 16) * 64u,
+                                  rowa + (xc.w & 0xffffu) * 64u, rowa + (xc.w >> 16) * 64u};
+        const unsigned mbits = (unsigned)hd.z >> (8 * hx);
         const float wl[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float mf[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
         float val[8];
         if (POOL == I2V_POOL_NONE) {
             // lattice == pooled grid: lattice row i is pooled row i
@@ -288,7 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         // columns that fall into the cell of the column before them carry that column's sum along
 #pragma unroll
-        for (int j = 1; j < G; ++j) val[j] = fmaf(mf[j], val[j - 1], val[j]);
+        for (int j = 1; j < G; ++j)
+            if ((mbits >> j) & 1u) val[j] += val[j - 1];
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);      // the stage's bytes are in registers now
         s += kGroups;
