@@ -33,14 +33,15 @@ struct alignas(16) PhaseTab {
     // (start, start + 1) that has parity h (a 16-bit cell index), and its weight (validity and the avg pool's 1/4 folded in)
     unsigned short xcell[2][8];
     float w[2][8];
-    float4 yrow[8];       // {start row * W * 64 bytes (int bits), 1 - fy, fy, position in its run (int bits; -1: invalid)}
-    int maxrun;           // longest run of lattice rows sharing a start row (0: nothing to scatter)
-    int rows_apart;       // 1: consecutive valid lattice rows start at least two feature rows apart (all 16 rows distinct)
-    unsigned merge;       // bit 8 h + j: for half-warp h, column j falls into the same cell as column j-1 (the two
-                          // contributions are then summed in registers)
-    int pad_;
+    // per lattice row: {start row * W * 64 bytes (int bits), 1 - fy, fy, packed (int bits)}.  packed: bits 0-3 position
+    // of the row in its run of equal start rows (15: row invalid), bits 4-7 the longest such run of the RoI (0: nothing
+    // to scatter), bit 8: consecutive valid lattice rows start at least two feature rows apart (all 16 rows distinct),
+    // bits 16-31: bit 8 h + j set when, for half-warp h, column j falls into the same cell as column j-1 (the two
+    // contributions are then summed in registers).  The RoI-wide fields are repeated in every row so that a warp needs
+    // one 16-byte load.
+    float4 yrow[8];
 };
-static_assert(sizeof(PhaseTab) == 240 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
+static_assert(sizeof(PhaseTab) == 224 && sizeof(PhaseTab) <= kRoiTabSlotBytes, "PhaseTab layout");
 
 namespace {
 
@@ -50,8 +51,8 @@ constexpr int kConsumers = 8 * kGroups;
 constexpr int kThreads = (kConsumers + 1) * 32;
 constexpr int kStages = 20;
 constexpr int kTileBytes = kK * 49 * 4;                 // 3136
-constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 240
-constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3376
+constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 224
+constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3360
 constexpr int kRingBytes = kStages * kStageBytes;
 constexpr int kBarBytes = ((2 * kStages * 8 + 127) / 128) * 128;
 static_assert(kStageBytes % 16 == 0, "ring layout");
@@ -103,12 +104,6 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
     PhaseTab q;
     const unsigned full = (1u << G) - 1u;
     const unsigned vx = t.valid_x & full, vy = t.valid_y & full;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const bool oky = (vy >> p) & 1u;
-        q.yrow[p] = make_float4(__int_as_float(oky ? t.y.start[p] * W * 64 : 0), oky ? 1.f - t.y.frac[p] : 0.f,
-                                oky ? t.y.frac[p] : 0.f, __int_as_float(oky ? (int)((t.y_runpos >> (4 * p)) & 15u) : -1));
-    }
     // Columns: starts are non-decreasing, so the cell of parity h under column j is non-decreasing in j too and equal
     // cells are consecutive.  Each lane sums a run of equal cells in registers (merge) and stores every column in order:
     // the last store of a run carries the whole sum and overwrites the partial ones before it (same thread, same
@@ -139,19 +134,25 @@ __global__ void __launch_bounds__(128) phase_prep_kernel(const LatticeRoi* __res
         }
     }
     const bool any = t.batch >= 0 && vx != 0u && vy != 0u;
-    q.maxrun = any ? (int)t.y_maxrun : 0;
+    const unsigned maxrun = any ? min(t.y_maxrun, 15u) : 0u;
+    unsigned apart = 1;
     {
-        int prev = -100, apart = 1;
+        int prev = -100;
 #pragma unroll
         for (int p = 0; p < 8; ++p)
             if ((vy >> p) & 1u) {
                 if (t.y.start[p] - prev < 2) apart = 0;
                 prev = t.y.start[p];
             }
-        q.rows_apart = apart;
     }
-    q.merge = mergebits;
-    q.pad_ = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const bool oky = (vy >> p) & 1u;
+        const unsigned packed = ((oky && any) ? ((t.y_runpos >> (4 * p)) & 15u) : 15u) | (maxrun << 4) |
+                                ((any ? apart : 0u) << 8) | (mergebits << 16);
+        q.yrow[p] = make_float4(__int_as_float(oky ? t.y.start[p] * W * 64 : 0), oky ? 1.f - t.y.frac[p] : 0.f,
+                                oky ? t.y.frac[p] : 0.f, __int_as_float((int)packed));
+    }
     ptab[n] = q;
 }
 
@@ -257,21 +258,22 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(full + s, round & 1);
         const unsigned char* stage = ring + s * kStageBytes;
         const PhaseTab* t = reinterpret_cast<const PhaseTab*>(stage + kTileBytes);
-        const int4 hd = *reinterpret_cast<const int4*>(&t->maxrun);    // {maxrun, rows_apart, merge bits, -}
-        const int maxrun = hd.x;
         const float4 yr = t->yrow[row];
+        const unsigned packed = (unsigned)__float_as_int(yr.w);
+        const int maxrun = (int)((packed >> 4) & 15u);
+        const bool rows_apart = (packed >> 8) & 1u;
         const uint4 xc = *reinterpret_cast<const uint4*>(t->xcell[hx]);         // eight 16-bit cell indices
         const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
         const float* ra = reinterpret_cast<const float*>(stage + ra_off);
         const float* rb = reinterpret_cast<const float*>(stage + rb_off);
-        const int runpos = (row < G) ? __float_as_int(yr.w) : -1;
+        const int runpos = (row < G) ? (int)(packed & 15u) : 15;      // 15: no such lattice row
         const float wy0 = yr.y, wy1 = yr.z;
         const unsigned rowa = lane_planes + (unsigned)__float_as_int(yr.x);
         const unsigned addr[8] = {rowa + (xc.x & 0xffffu) * 64u, rowa + (xc.x >> 16) * 64u,
                                   rowa + (xc.y & 0xffffu) * 64u, rowa + (xc.y >> 16) * 64u,
                                   rowa + (xc.z & 0xffffu) * 64u, rowa + (xc.z >> 16) * 64u,
                                   rowa + (xc.w & 0xffffu) * 64u, rowa + (xc.w >> 16) * 64u};
-        const unsigned mbits = (unsigned)hd.z >> (8 * hx);
+        const unsigned mbits = packed >> (16 + 8 * hx);
         const float wl[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         float val[8];
         if (POOL == I2V_POOL_NONE) {
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         // ---- scatter, after RoI k-1 ----
         if (k > 0) bar_sync(bar_prev, 512);
-        if (hd.y) {
+        if (rows_apart) {
             // tall RoI: the sixteen feature rows under the eight lattice rows are all different, one phase will do
             if (runpos == 0) {
                 float oa[8], ob[8];
