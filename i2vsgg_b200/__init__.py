@@ -24,7 +24,7 @@ _MODEL_MODULES = [
     "model.roi_pooling.modules", "model.roi_pooling.modules.roi_pool",
     "model.nms", "model.nms.nms_wrapper", "model.nms.nms_gpu",
     "model.rpn", "model.rpn.generate_anchors", "model.rpn.proposal_layer", "model.rpn.proposal_target_layer_cascade",
-    "model.rpn.anchor_target_layer",
+    "model.rpn.anchor_target_layer", "model.rpn.rpn",
     "model.roi_layers", "model.roi_layers.roi_align", "model.roi_layers.roi_pool", "model.roi_layers.nms",
 ]
 

@@ -27,6 +27,33 @@ namespace i2v {
 // bbox_transform.py:77-103 with every operation rounded separately; exp evaluated in double and rounded once
 // (CUDA's double exp is < 1 ulp in double, so the float result is the correctly rounded one, which is what the
 // oracle computes with glibc).
+// The RPN head's 2-way softmax (rpn.py:63-69: scores [B,2A,H,W] viewed as [B,2,A*H,W], softmax over dim 1): channel a
+// is an anchor's background score, channel a + A its foreground score.  Every step is one rounded fp32 operation and the
+// exponentials are the correctly rounded ones (double exp rounded once), so the oracle reproduces the bits.
+__device__ __forceinline__ void softmax2(float s_bg, float s_fg, float& p_bg, float& p_fg) {
+    const float m = fmaxf(s_bg, s_fg);
+    const float e_bg = (float)exp((double)__fsub_rn(s_bg, m)), e_fg = (float)exp((double)__fsub_rn(s_fg, m));
+    const float sum = __fadd_rn(e_bg, e_fg);
+    p_bg = __fdiv_rn(e_bg, sum);
+    p_fg = __fdiv_rn(e_fg, sum);
+}
+
+__global__ void __launch_bounds__(256) rpn_cls_prob_kernel(const float* __restrict__ score, float* __restrict__ prob,
+                                                           int B, int A, int HW) {
+    const int64_t total = (int64_t)B * A * HW;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / ((int64_t)A * HW), r = idx - b * (int64_t)A * HW;      // r = a * HW + pixel
+        const size_t bg = (size_t)b * 2 * A * HW + (size_t)r, fg = bg + (size_t)A * HW;
+        float p0, p1;
+        softmax2(__ldg(score + bg), __ldg(score + fg), p0, p1);
+        prob[bg] = p0;
+        prob[fg] = p1;
+    }
+}
+
+// SCORES: `cls_prob` holds the raw RPN scores and the foreground probability is formed here (rpn.py:63-69 fused in)
+template <bool SCORES>
 __global__ void __launch_bounds__(256) proposal_decode_kernel(const float* __restrict__ cls_prob,
                                                               const float* __restrict__ bbox_pred,
                                                               const float* __restrict__ im_info,
@@ -63,7 +90,16 @@ __global__ void __launch_bounds__(256) proposal_decode_kernel(const float* __res
             o.w = fminf(fmaxf(y2, 0.f), ymax);
             reinterpret_cast<float4*>(boxes)[j] = o;
         }
-        if (scores) scores[j] = __ldg(cls_prob + ((size_t)b * 2 * A + A + a) * HW + pix);
+        if (scores) {
+            const float* fg = cls_prob + ((size_t)b * 2 * A + A + a) * HW + pix;
+            if (SCORES) {
+                float p0, p1;
+                softmax2(__ldg(fg - (size_t)A * HW), __ldg(fg), p0, p1);
+                scores[j] = p1;
+            } else {
+                scores[j] = __ldg(fg);
+            }
+        }
     }
 }
 
@@ -519,11 +555,11 @@ static int proposal_common(const float* cls_prob, const float* bbox_pred, const 
     return I2V_OK;
 }
 
-extern "C" int i2v_proposal_forward(const float* cls_prob, const float* bbox_pred, const float* im_info,
-                                    const float* base_anchors, int batch, int num_anchors, int height, int width,
-                                    int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
-                                    float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
-                                    cudaStream_t stream) {
+static int proposal_forward_impl(bool from_scores, const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                 const float* base_anchors, int batch, int num_anchors, int height, int width,
+                                 int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                                 float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t stream) {
     NmsWs w;
     int ka;
     I2V_TRY(proposal_common(cls_prob, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width, feat_stride,
@@ -532,8 +568,12 @@ extern "C" int i2v_proposal_forward(const float* cls_prob, const float* bbox_pre
     if (batch == 0) return I2V_OK;
     I2V_REQUIRE(out_rois, "proposal_forward: null out_rois");
     int64_t total = (int64_t)batch * ka;
-    proposal_decode_kernel<<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
-                                                                     num_anchors, height, width, feat_stride, w.boxes, w.scores);
+    if (from_scores)
+        proposal_decode_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
+                                                                               num_anchors, height, width, feat_stride, w.boxes, w.scores);
+    else
+        proposal_decode_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
+                                                                                num_anchors, height, width, feat_stride, w.boxes, w.scores);
     I2V_TRY(check_launch("proposal_decode_kernel"));
     I2V_TRY(launch_sort(w.scores, batch, ka, 1, ka, w, stream));
     NmsArgs a{};
@@ -557,6 +597,39 @@ extern "C" int i2v_proposal_forward(const float* cls_prob, const float* bbox_pre
     return launch_nms(a, batch, stream);
 }
 
+extern "C" int i2v_proposal_forward(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                    const float* base_anchors, int batch, int num_anchors, int height, int width,
+                                    int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                                    float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
+    return proposal_forward_impl(false, cls_prob, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width,
+                                 feat_stride, pre_nms_top_n, post_nms_top_n, nms_thresh, out_rois, out_counts, workspace,
+                                 workspace_bytes, stream);
+}
+
+// rpn.py:63-78: the same layer fed with the RPN head's raw class scores; the 2-way softmax and the foreground slice are
+// folded into the decode kernel (no [B,2A,H,W] probability tensor is written or re-read)
+extern "C" int i2v_proposal_forward_scores(const float* cls_score, const float* bbox_pred, const float* im_info,
+                                           const float* base_anchors, int batch, int num_anchors, int height, int width,
+                                           int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                                           float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                                           cudaStream_t stream) {
+    return proposal_forward_impl(true, cls_score, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width,
+                                 feat_stride, pre_nms_top_n, post_nms_top_n, nms_thresh, out_rois, out_counts, workspace,
+                                 workspace_bytes, stream);
+}
+
+// rpn.py:66-68: rpn_cls_prob [B,2A,H,W] from rpn_cls_score [B,2A,H,W] (softmax over (a, a + A) pairs)
+extern "C" int i2v_rpn_cls_prob(const float* cls_score, float* cls_prob, int batch, int num_anchors, int height,
+                                int width, cudaStream_t stream) {
+    I2V_REQUIRE(batch >= 0 && num_anchors >= 1 && height >= 1 && width >= 1, "rpn_cls_prob: bad size");
+    if (batch == 0) return I2V_OK;
+    I2V_REQUIRE(cls_score && cls_prob, "rpn_cls_prob: null pointer");
+    const int64_t total = (int64_t)batch * num_anchors * height * width;
+    rpn_cls_prob_kernel<<<grid_for(total, 256), 256, 0, stream>>>(cls_score, cls_prob, batch, num_anchors, height * width);
+    return check_launch("rpn_cls_prob_kernel");
+}
+
 extern "C" int i2v_proposal_stages(const float* cls_prob, const float* bbox_pred, const float* im_info,
                                    const float* base_anchors, int batch, int num_anchors, int height, int width,
                                    int feat_stride, float* boxes, float* scores, int* order, void* workspace,
@@ -567,7 +640,7 @@ extern "C" int i2v_proposal_stages(const float* cls_prob, const float* bbox_pred
                             workspace, workspace_bytes, w, ka));
     if (batch == 0) return I2V_OK;
     int64_t total = (int64_t)batch * ka;
-    proposal_decode_kernel<<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
+    proposal_decode_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
                                                                      num_anchors, height, width, feat_stride, w.boxes, w.scores);
     I2V_TRY(check_launch("proposal_decode_kernel"));
     if (boxes) I2V_CUDA_TRY(cudaMemcpyAsync(boxes, w.boxes, sizeof(float) * 4 * (size_t)total, cudaMemcpyDeviceToDevice, stream));

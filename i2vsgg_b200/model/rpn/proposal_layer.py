@@ -18,7 +18,9 @@ class _ProposalLayer(nn.Module):
         self._anchors = torch.from_numpy(generate_anchors(scales=np.array(scales), ratios=np.array(ratios))).float()
         self._num_anchors = self._anchors.size(0)
 
-    def forward(self, input, target=False):
+    def forward(self, input, target=False, from_scores=False):
+        """`input` as in the reference: (rpn_cls_prob, rpn_bbox_pred, im_info, cfg_key).  With `from_scores` the first
+        entry is the raw rpn_cls_score and the softmax of rpn.py:66-68 runs inside the decode kernel (model/rpn/rpn.py)."""
         cls_prob, bbox_deltas, im_info, cfg_key = input[0], input[1], input[2], input[3]
         pre_nms_topN = cfg[cfg_key].RPN_PRE_NMS_TOP_N
         post_nms_topN = cfg[cfg_key].RPN_POST_NMS_TOP_N
@@ -29,7 +31,8 @@ class _ProposalLayer(nn.Module):
             self._anchors = self._anchors.to(cls_prob.device)
         with torch.no_grad():
             return ops.proposal_forward(cls_prob, bbox_deltas, im_info, self._anchors, int(self._feat_stride),
-                                        int(pre_nms_topN), int(post_nms_topN), float(nms_thresh))
+                                        int(pre_nms_topN), int(post_nms_topN), float(nms_thresh),
+                                        from_scores=from_scores)
 
     def backward(self, top, propagate_down, bottom):
         """This layer does not propagate gradients."""

@@ -174,9 +174,23 @@ def nms_dets(dets, thresh: float):
 
 
 # --------------------------------------------------------------------------------------- proposal layer
+def rpn_cls_prob(cls_score):
+    """rpn.py:66-68: rpn_cls_prob [B,2A,H,W] = softmax over each anchor's (background, foreground) channel pair."""
+    cls_score = _f32(cls_score, "cls_score")
+    B, A2, H, W = cls_score.shape
+    if A2 % 2:
+        raise _lib.I2VError("rpn_cls_prob: the channel count must be even (2 per anchor)")
+    out = torch.empty_like(cls_score)
+    lib = load()
+    with torch.cuda.device(cls_score.device):
+        check(lib.i2v_rpn_cls_prob(_p(cls_score), _p(out), B, A2 // 2, H, W, _stream()), "i2v_rpn_cls_prob")
+    return out
+
+
 def proposal_forward(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: int, pre_nms_top_n: int,
-                     post_nms_top_n: int, nms_thresh: float, return_counts: bool = False):
-    """_ProposalLayer.forward (proposal_layer.py:49-163) -> rois [B, post_nms_top_n, 5]."""
+                     post_nms_top_n: int, nms_thresh: float, return_counts: bool = False, from_scores: bool = False):
+    """_ProposalLayer.forward (proposal_layer.py:49-163) -> rois [B, post_nms_top_n, 5].  With `from_scores` the first
+    argument is the RPN head's raw rpn_cls_score and the softmax of rpn.py:66-68 runs inside the decode kernel."""
     cls_prob, bbox_pred = _f32(cls_prob, "cls_prob"), _f32(bbox_pred, "bbox_pred")
     im_info, base_anchors = _f32(im_info, "im_info"), _f32(base_anchors, "base_anchors")
     B, A2, H, W = cls_prob.shape
@@ -188,9 +202,10 @@ def proposal_forward(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: in
     lib = load()
     with torch.cuda.device(cls_prob.device):
         ws = _workspace(lib.i2v_proposal_workspace_bytes(B, A, H, W, pre_nms_top_n), cls_prob.device)
-        check(lib.i2v_proposal_forward(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(base_anchors), B, A, H, W,
-                                       int(feat_stride), int(pre_nms_top_n), int(post_nms_top_n), float(nms_thresh),
-                                       _p(out), _p(counts), _p(ws), ws.numel(), _stream()), "i2v_proposal_forward")
+        fn = lib.i2v_proposal_forward_scores if from_scores else lib.i2v_proposal_forward
+        check(fn(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(base_anchors), B, A, H, W,
+                 int(feat_stride), int(pre_nms_top_n), int(post_nms_top_n), float(nms_thresh),
+                 _p(out), _p(counts), _p(ws), ws.numel(), _stream()), "i2v_proposal_forward")
     return (out, counts) if return_counts else out
 
 

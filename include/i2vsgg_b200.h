@@ -138,6 +138,17 @@ int i2v_proposal_forward(const float* cls_prob, const float* bbox_pred, const fl
                          int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
                          float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
+/* The step before the layer (rpn.py:63-78): rpn_cls_score [B,2A,H,W] -> rpn_cls_prob [B,2A,H,W], the softmax over each
+ * anchor's (background, foreground) pair of channels (a, a+A). */
+int i2v_rpn_cls_prob(const float* cls_score, float* cls_prob, int batch, int num_anchors, int height, int width,
+                     cudaStream_t stream);
+/* i2v_proposal_forward fed with the raw scores: softmax and foreground slice fused into the decode kernel; the result
+ * equals i2v_rpn_cls_prob followed by i2v_proposal_forward bit for bit. */
+int i2v_proposal_forward_scores(const float* cls_score, const float* bbox_pred, const float* im_info,
+                                const float* base_anchors, int batch, int num_anchors, int height, int width,
+                                int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                                float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                                cudaStream_t stream);
 /* Stage outputs for tests: decoded+clipped boxes [B,KA,4], scores [B,KA] in anchor-major order, and (after
  * the sort) order [B,KA] int32 = candidate indices by descending score.  Any of the three may be NULL. */
 int i2v_proposal_stages(const float* cls_prob, const float* bbox_pred, const float* im_info,

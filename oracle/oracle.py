@@ -218,6 +218,21 @@ def generate_anchors(base_size=16, ratios=(0.5, 1, 2), scales=(8, 16, 32)) -> np
     return np.asarray(rows, np.float64)
 
 
+def rpn_cls_prob(cls_score) -> np.ndarray:
+    """rpn.py:63-69: rpn_cls_score [B,2A,H,W] viewed as [B,2,A*H,W], softmax over dim 1, viewed back: channel a is an
+    anchor's background score, channel a + A its foreground score.  fp32 max / subtract / add / divide, exponentials
+    correctly rounded (double exp rounded once) -- the arithmetic the CUDA kernel performs, so it matches bit for bit;
+    torch's own softmax (vectorised expf) differs from it by at most a few ulp (tests/golden/rpn_golden.npz)."""
+    s = _f32(cls_score)
+    A = s.shape[1] // 2
+    bg, fg = s[:, :A], s[:, A:]
+    m = np.maximum(bg, fg)
+    e_bg = np.exp((bg - m).astype(np.float64)).astype(np.float32)
+    e_fg = np.exp((fg - m).astype(np.float64)).astype(np.float32)
+    tot = e_bg + e_fg
+    return np.concatenate([e_bg / tot, e_fg / tot], axis=1).astype(np.float32)
+
+
 def proposal_decode(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: int = 16):
     """proposal_layer.py:67,81-111 + bbox_transform.py:77-103,125-133 -> (boxes [B,KA,4], scores [B,KA])."""
     cls_prob, bbox_pred, im_info = _f32(cls_prob), _f32(bbox_pred), _f32(im_info)

@@ -334,3 +334,23 @@ def py_anchor_target_layer(gt_boxes, im_info, feat_h=38, feat_w=63, seed=0):
     with torch.no_grad():
         out = layer((score, gt, torch.from_numpy(np.ascontiguousarray(im_info, np.float32)), None))
     return [o.numpy() for o in out]
+
+
+def py_rpn_cls_prob(cls_score: np.ndarray) -> np.ndarray:
+    """Executes rpn.py:66-68 on the CPU: `_RPN.reshape` (rpn.py:46-55, taken from the unmodified source file) around
+    `F.softmax(., 1)`.  Only the static method is extracted: the class body needs the cffi-era extensions to import."""
+    import ast
+    import torch
+    import torch.nn.functional as F
+    src = open(os.path.join(REF_ROOT, "lib/model/rpn/rpn.py")).read()
+    fn = next(n for c in ast.walk(ast.parse(src)) if isinstance(c, ast.ClassDef) and c.name == "_RPN"
+              for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "reshape")
+    fn.decorator_list = []
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "rpn.py:_RPN.reshape", "exec"), ns)
+    reshape = ns["reshape"]
+    x = torch.from_numpy(np.ascontiguousarray(cls_score, np.float32))
+    nc_score_out = x.shape[1]
+    with torch.no_grad():
+        prob = reshape(F.softmax(reshape(x, 2), 1), nc_score_out)
+    return prob.numpy()

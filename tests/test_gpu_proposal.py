@@ -1,5 +1,7 @@
 """GPU parity tests (B200 box): proposal decode, sort, NMS and the fused proposal layer through the C ABI against the
 oracle (bit-exact indices) and against the golden vectors written from the reference's own Python."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -213,3 +215,47 @@ def test_pipelined_step_equals_device_step():
         torch.cuda.synchronize()
         for a, w in zip(got, want[k]):
             assert torch.equal(a, w)
+
+
+def test_rpn_cls_prob_matches_oracle_bit_for_bit(ops, orc):
+    """rpn.py:66-68 on the device: the oracle performs the same rounded operations, so the bits agree; the executed
+    reference (torch softmax) is within a few ulp (golden fixture)."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rpn_golden.npz"))
+    for name in ("small", "wide", "a3"):
+        score = gold[f"{name}_score"]
+        got = ops.rpn_cls_prob(cuda(score)).cpu().numpy()
+        assert np.array_equal(got, orc.rpn_cls_prob(score))
+        np.testing.assert_allclose(got, gold[f"{name}_prob"], rtol=5e-7, atol=1e-38)
+    rng = np.random.default_rng(4)
+    big = (rng.standard_normal((4, 18, 38, 63)) * 4).astype(np.float32)
+    assert np.array_equal(ops.rpn_cls_prob(cuda(big)).cpu().numpy(), orc.rpn_cls_prob(big))
+
+
+def test_proposals_from_raw_scores_equal_the_two_step_path(ops, orc):
+    """Softmax fused into the decode kernel == rpn_cls_prob followed by the proposal layer, and both equal the oracle's
+    proposal layer run on the oracle's probabilities."""
+    rng = np.random.default_rng(9)
+    B = 3
+    score = (rng.standard_normal((B, 18, 38, 63)) * 2.5).astype(np.float32)
+    _, reg = synth.rpn_outputs(31, batch=B)
+    info, anchors = synth.im_info(B), synth.BASE_ANCHORS
+    fused = ops.proposal_forward(cuda(score), cuda(reg), cuda(info), cuda(anchors), 16, 6000, 300, 0.7, from_scores=True)
+    prob = ops.rpn_cls_prob(cuda(score))
+    two_step = ops.proposal_forward(prob, cuda(reg), cuda(info), cuda(anchors), 16, 6000, 300, 0.7)
+    assert torch.equal(fused, two_step)
+    want = orc.proposal_layer(orc.rpn_cls_prob(score), reg, info, 6000, 300, 0.7)
+    assert np.array_equal(fused.cpu().numpy(), want)
+
+
+def test_rpn_module_mirror(ops):
+    from i2vsgg_b200.model.rpn.rpn import _RPN
+    rng = np.random.default_rng(10)
+    score = cuda((rng.standard_normal((2, 18, 38, 63)) * 2).astype(np.float32))
+    _, reg = synth.rpn_outputs(32, batch=2)
+    rpn = _RPN(1024).eval()
+    a = rpn.forward_head_outputs(score, cuda(reg), cuda(synth.im_info(2)))
+    b = rpn.forward_head_outputs(score, cuda(reg), cuda(synth.im_info(2)), fused=False)
+    assert a.shape == (2, 300, 5) and torch.equal(a, b)
+    p = _RPN.cls_prob(score)
+    ref = torch.softmax(_RPN.reshape(score, 2), 1).view_as(score)
+    assert float((p - ref).abs().max()) < 1e-6
