@@ -169,3 +169,32 @@ def test_conv2d_nhwc_implicit_gemm_matches_torch(ops, c, o, h, k, stride, pad):
     want = torch.relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad))
     assert y.shape == (n, want.shape[2], want.shape[3], o)
     assert float((y.permute(0, 3, 1, 2).double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(1, 1024, 38, 63), (2, 64, 63, 38)])   # config-3 frame; portrait map (pitch 41)
+def test_roi_pool_rows_bf16_planes_equal_fp32_planes(ops, shape):
+    """The bf16-plane kernel (two channels per word, max.bf16x2) against the fp32-plane kernel rounded at the end and the
+    exact RoIPool op: rounding to bf16 is monotone, so all three agree bit for bit -- union boxes of every size, tiny
+    boxes, boxes over the border and stray frame indices included."""
+    import os
+    from i2vsgg_b200._lib import ARGMAX_PLANE
+    B, C, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    feat = torch.randn(shape, device="cuda", generator=g) * 3
+    rng = np.random.default_rng(H)
+    N = 700
+    iw, ih = W * 16.0, H * 16.0
+    x1 = rng.uniform(-40, iw - 20, N); y1 = rng.uniform(-40, ih - 20, N)
+    w = rng.choice([4.0, 30.0, 90.0, 250.0, 600.0, 1100.0], N); h = rng.choice([4.0, 30.0, 90.0, 250.0, 600.0], N)
+    r = np.stack([rng.integers(0, B, N), x1, y1, np.minimum(x1 + w, iw + 30), np.minimum(y1 + h, ih + 30)], 1).astype(np.float32)
+    r[5, 0], r[6, 0] = -1, B + 3
+    rois = torch.from_numpy(r).cuda()
+    got = ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16)
+    os.environ["I2V_POOL_F32_PLANES"] = "1"
+    try:
+        ref = ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16)
+    finally:
+        del os.environ["I2V_POOL_F32_PLANES"]
+    assert torch.equal(got, ref)
+    want, _ = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16, ARGMAX_PLANE)
+    assert torch.equal(got, want.reshape(N, -1).bfloat16())
