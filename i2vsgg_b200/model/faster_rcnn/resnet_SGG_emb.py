@@ -137,8 +137,8 @@ class vrd(nn.Module):
         # roi_pool of objects and unions -> one bf16 matrix; fc6 / fc7 over all rows at once (:144-149, :158-163)
         k6 = self.in_channels * ps * ps
         pooled = torch.empty((n_obj + n_uni, k6), dtype=torch.bfloat16, device=dev)
-        ops.roi_pool_rows(fmap, boxes, ps, ps, self.spatial_scale, out=pooled[:n_obj])
-        ops.roi_pool_rows(fmap, pool_boxes, ps, ps, self.spatial_scale, out=pooled[n_obj:])
+        # one launch for both box sets: the feature planes are staged in shared memory once per CTA
+        ops.roi_pool_rows(fmap, torch.cat((boxes, pool_boxes)), ps, ps, self.spatial_scale, out=pooled)
         h = self.fc7(self.fc6(pooled))
         obj_feature = self.so_vis_embeddings(h[:n_obj], out_dtype=torch.float32)            # :150
 
