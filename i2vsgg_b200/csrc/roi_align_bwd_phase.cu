@@ -22,7 +22,7 @@
 //     a named barrier (the finishing group arrives, the next group waits) keeps the scatters in list order, so the
 //     result is bit-reproducible.
 //
-// Measured on config 2 (profiles/README.md): 1.59 ms against 2.28 ms; what binds it is the serial chain of scatter
+// Measured on config 2 (profiles/README.md): 1.54 ms against 2.28 ms; what binds it is the serial chain of scatter
 // phases (about 760 cycles per RoI against 256 cycles of shared-memory wavefronts) and, right behind it, the ring feed.
 #include "common.cuh"
 

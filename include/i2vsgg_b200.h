@@ -177,7 +177,9 @@ int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* c
 #define I2V_DT_BF16 1  /* bf16 storage; tensor-core operands under tcgen05 kind::f16           */
 #define I2V_DT_TF32 2  /* fp32 storage consumed by the tensor cores as tf32 (kind::tf32)       */
 /* roi_pool(fmap, boxes).view(N, -1) of resnet_SGG_emb.py:144-146,158-160: the model._C RoIPool values (no
- * arg-max) written as rows [N, C*ph*pw] with pitch ldo (elements), fp32 or rounded once to bf16. */
+ * arg-max) written as rows [N, C*ph*pw] with pitch ldo (elements), fp32 or rounded once to bf16.  The bf16 flavour keeps
+ * its shared-memory planes in bf16 (two channels per word; rounding is monotone, so the rows equal the fp32 kernel's bit
+ * for bit); the environment variable I2V_POOL_F32_PLANES=1 forces fp32 planes (tests compare the two). */
 int i2v_roi_pool_rows(const float* features, const float* rois, void* out, int batch, int channels, int height,
                       int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
                       int out_dtype, cudaStream_t stream);
