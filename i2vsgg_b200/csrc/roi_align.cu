@@ -153,24 +153,25 @@ __global__ void __launch_bounds__(256) roi_bucket_kernel(const int* __restrict__
         if (b == batch - 1) starts[batch] = s + counts[b];
     }
     __syncthreads();
-    int base = s_base;
-    for (int i0 = 0; i0 < num_rois; i0 += 256) {
-        int i = i0 + tid;
-        bool mine = (i < num_rois) && (roi_batch[i] == b);
-        unsigned m = __ballot_sync(0xffffffffu, mine);
-        __syncthreads();  // s_warp reuse
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            int c = s_warp[w];
-            if (w < warp) before += c;
-            total += c;
-        }
-        if (mine) order[base + before + __popc(m & ((1u << lane) - 1u))] = i;
-        base += total;
+    // Each thread owns a contiguous chunk of the RoI indices, counts its matches, takes its offset from one block-wide
+    // exclusive scan and writes them in ascending order: two barriers in all, instead of two per 256 RoIs.
+    const int chunk = (num_rois + 255) / 256;
+    const int lo = min(tid * chunk, num_rois), hi = min(lo + chunk, num_rois);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) mine += (__ldg(roi_batch + i) == b);
+    int incl = mine;                                    // inclusive scan inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    __syncthreads();                                    // s_warp reuse
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    int pos = s_base + before + incl - mine;
+    for (int i = lo; i < hi; ++i)
+        if (__ldg(roi_batch + i) == b) order[pos++] = i;
 }
 
 // ------------------------------------------------------------------------------------------ gather forward
