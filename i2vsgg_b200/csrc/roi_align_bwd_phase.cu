@@ -54,7 +54,7 @@ constexpr int kTileBytes = kK * 49 * 4;                 // 3136
 constexpr int kTabBytes = (int)sizeof(PhaseTab);        // 224
 constexpr int kStageBytes = kTileBytes + kTabBytes;     // 3360
 constexpr int kRingBytes = kStages * kStageBytes;
-constexpr int kBarBytes = ((2 * kStages * 8 + 127) / 128) * 128;
+constexpr int kBarBytes = ((2 * kStages * 8 + 32 + 127) / 128) * 128;    // barriers + 32 bytes of zeros (a pooled row outside the grid)
 static_assert(kStageBytes % 16 == 0, "ring layout");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 8) reinterpret_cast<float*>(empty + kStages)[tid] = 0.f;
     {
         float4* z = reinterpret_cast<float4*>(planes);
         for (int i = tid; i < HW * kK / 4; i += kThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,9 +247,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int hx = lane >> 4, c = lane & 15;     // hx: parity of the cells this half-warp owns
     const int row_bytes = W * 64;
     const unsigned lane_planes = smem_u32(planes) + c * 4;
+    // pooled rows under lattice row `row`: rows i-1 and i for the avg pool, row i without a pool; a row outside the 7x7
+    // grid (and the unused upper row of the pool-less lattice) reads the zero row instead
     const int ra_off = (c * 49 + max(row - 1, 0) * P) * 4, rb_off = (c * 49 + min(row, P - 1) * P) * 4;
-    const float ma = (POOL == I2V_POOL_NONE) ? 0.f : (row >= 1 ? 1.f : 0.f);
-    const float mb = row < P ? 1.f : 0.f;
+    const bool has_a = (POOL != I2V_POOL_NONE) && row >= 1, has_b = row < P;
+    const float* zero_row = reinterpret_cast<const float*>(empty + kStages);
     const int bar_prev = 2 + (grp + kGroups - 1) % kGroups, bar_mine = 2 + grp, bar_intra = 2 + kGroups + grp;
 
     int s = grp % kStages;
@@ -264,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const bool rows_apart = (packed >> 8) & 1u;
         const uint4 xc = *reinterpret_cast<const uint4*>(t->xcell[hx]);         // eight 16-bit cell indices
         const float4 w0 = *reinterpret_cast<const float4*>(t->w[hx]), w1 = *reinterpret_cast<const float4*>(t->w[hx] + 4);
-        const float* ra = reinterpret_cast<const float*>(stage + ra_off);
-        const float* rb = reinterpret_cast<const float*>(stage + rb_off);
+        const float* ra = has_a ? reinterpret_cast<const float*>(stage + ra_off) : zero_row;
+        const float* rb = has_b ? reinterpret_cast<const float*>(stage + rb_off) : zero_row;
         const int runpos = (row < G) ? (int)(packed & 15u) : 15;      // 15: no such lattice row
         const float wy0 = yr.y, wy1 = yr.z;
         const unsigned rowa = lane_planes + (unsigned)__float_as_int(yr.x);
@@ -279,13 +282,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (POOL == I2V_POOL_NONE) {
             // lattice == pooled grid: lattice row i is pooled row i
 #pragma unroll
-            for (int j = 0; j < P; ++j) val[j] = rb[j] * mb * wl[j];
+            for (int j = 0; j < P; ++j) val[j] = rb[j] * wl[j];
             val[7] = 0.f;
         } else {
             // lattice row i collects the pooled rows i-1 and i, lattice column j the pooled columns j-1 and j
             float sj[P];
 #pragma unroll
-            for (int j = 0; j < P; ++j) sj[j] = ra[j] * ma + rb[j] * mb;
+            for (int j = 0; j < P; ++j) sj[j] = ra[j] + rb[j];
             val[0] = sj[0] * wl[0];
 #pragma unroll
             for (int j = 1; j < P; ++j) val[j] = (sj[j - 1] + sj[j]) * wl[j];
