@@ -167,13 +167,27 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
 }
 // One feature row of one lattice row: the lane's eight cells += val[j] * wy.  All eight loads are issued before the
 // first store; columns that share a cell hold running sums, so storing in column order leaves the complete one.
+// Packed fp32x2 fused multiply-add (FFMA2): two lattice columns per instruction.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+    asm("{.reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %4};\n"
+        "mov.b64 rc, {%5, %6};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
 template <int G>
 __device__ __forceinline__ void scatter_row(const unsigned (&addr)[8], unsigned row_off, const float (&val)[8], float wy) {
-    float o[8];
+    float o[8], n[8];
 #pragma unroll
     for (int j = 0; j < G; ++j) o[j] = lds_f32(addr[j] + row_off);
 #pragma unroll
-    for (int j = 0; j < G; ++j) sts_f32(addr[j] + row_off, fmaf(val[j], wy, o[j]));
+    for (int j = 0; j + 1 < G; j += 2) ffma2(n[j], n[j + 1], val[j], val[j + 1], wy, o[j], o[j + 1]);
+    if (G & 1) n[G - 1] = fmaf(val[G - 1], wy, o[G - 1]);
+#pragma unroll
+    for (int j = 0; j < G; ++j) sts_f32(addr[j] + row_off, n[j]);
 }
 
 template <int POOL, int WT>
@@ -295,9 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             val[7] = sj[P - 1] * wl[7];
         }
         // columns that fall into the cell of the column before them carry that column's sum along
+        if (mbits & 0xfeu) {                          // uniform per half-warp; most RoIs are wide enough to have none
 #pragma unroll
-        for (int j = 1; j < G; ++j)
-            if ((mbits >> j) & 1u) val[j] += val[j - 1];
+            for (int j = 1; j < G; ++j)
+                if ((mbits >> j) & 1u) val[j] += val[j - 1];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);      // the stage's bytes are in registers now
         s += kGroups;
@@ -310,15 +326,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (rows_apart) {
             // tall RoI: the sixteen feature rows under the eight lattice rows are all different, one phase will do
             if (runpos == 0) {
-                float oa[8], ob[8];
+                float oa[8], ob[8], na[8], nb[8];
 #pragma unroll
                 for (int j = 0; j < G; ++j) oa[j] = lds_f32(addr[j]);
 #pragma unroll
                 for (int j = 0; j < G; ++j) ob[j] = lds_f32(addr[j] + (unsigned)row_bytes);
 #pragma unroll
-                for (int j = 0; j < G; ++j) sts_f32(addr[j], fmaf(val[j], wy0, oa[j]));
+                for (int j = 0; j + 1 < G; j += 2) {
+                    ffma2(na[j], na[j + 1], val[j], val[j + 1], wy0, oa[j], oa[j + 1]);
+                    ffma2(nb[j], nb[j + 1], val[j], val[j + 1], wy1, ob[j], ob[j + 1]);
+                }
+                if (G & 1) {
+                    na[G - 1] = fmaf(val[G - 1], wy0, oa[G - 1]);
+                    nb[G - 1] = fmaf(val[G - 1], wy1, ob[G - 1]);
+                }
 #pragma unroll
-                for (int j = 0; j < G; ++j) sts_f32(addr[j] + (unsigned)row_bytes, fmaf(val[j], wy1, ob[j]));
+                for (int j = 0; j < G; ++j) sts_f32(addr[j], na[j]);
+#pragma unroll
+                for (int j = 0; j < G; ++j) sts_f32(addr[j] + (unsigned)row_bytes, nb[j]);
             }
         } else
         for (int r = 0; r < maxrun; ++r) {          // maxrun == 0: nothing to scatter (uniform over the CTA)
