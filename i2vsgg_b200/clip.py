@@ -15,9 +15,36 @@ from . import ops, sgg, shard
 
 
 class ClipRunner:
-    def __init__(self, head, im_h: float, im_w: float, frames_per_group: int = 4, top_k: int = shard.TOP_K):
+    def __init__(self, head, im_h: float, im_w: float, frames_per_group: int = 4, top_k: int = shard.TOP_K,
+                 graphs: bool = False):
+        """`graphs`: capture the ~150 launches of a frame group in a CUDA graph per (frames, detections) shape and replay it
+        for every later group of that shape (the group is launch-bound on the host otherwise)."""
         self.head, self.im_h, self.im_w = head, float(im_h), float(im_w)
         self.group, self.top_k = int(frames_per_group), int(top_k)
+        self.graphs = bool(graphs)
+        self._captured = {}
+
+    def _group_replayed(self, fmap, boxes, classes, conf):
+        """`_group` through a CUDA graph: static input buffers are overwritten, the graph replayed, the outputs copied out."""
+        key = (tuple(fmap.shape), tuple(boxes.shape), fmap.device.index)
+        entry = self._captured.get(key)
+        if entry is None:
+            static = [t.clone() for t in (fmap, boxes, classes, conf)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # lazy initialisation (caches, function attributes) first
+                for _ in range(2):
+                    self._group(*static)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._group(*static)
+            entry = self._captured[key] = (graph, static, out)
+        graph, static, out = entry
+        for dst, src in zip(static, (fmap, boxes, classes, conf)):
+            dst.copy_(src)
+        graph.replay()
+        return out[0].clone(), out[1].clone()
 
     def _group(self, fmap, boxes, classes, conf):
         """fmap [F,C,H,W], boxes [F,N,4], classes [F,N], conf [F,N] (device) -> records [F,top_k,13], counts [F]."""
@@ -59,7 +86,8 @@ class ClipRunner:
         recs, cnts = [], []
         for f0 in range(0, hi - lo, self.group):
             f1 = min(hi - lo, f0 + self.group)
-            r, c = self._group(fmaps[f0:f1], boxes[f0:f1], classes[f0:f1], conf[f0:f1])
+            step = self._group_replayed if self.graphs else self._group
+            r, c = step(fmaps[f0:f1], boxes[f0:f1], classes[f0:f1], conf[f0:f1])
             recs.append(r)
             cnts.append(c)
         dev = fmaps.device

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--det", type=int, default=64)
     ap.add_argument("--group", type=int, default=4)
+    ap.add_argument("--graphs", action="store_true", help="replay each frame group as a CUDA graph and check it against the eager run")
     ap.add_argument("--associate", action="store_true", help="rank 0 also runs the temporal association on the gathered records")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -50,9 +51,13 @@ def main():
     conf = torch.from_numpy(np.tile(conf, (hi - lo, 1))).to(dev)
     fmap1 = torch.from_numpy(synth.feature_map(100 + rank, 1)).to(dev)
     fmaps = fmap1.expand(hi - lo, -1, -1, -1)
-    runner = ClipRunner(head, synth.IM_H, synth.IM_W, a.group)
+    runner = ClipRunner(head, synth.IM_H, synth.IM_W, a.group, graphs=a.graphs)
     warm = min(hi - lo, a.group)
-    runner._group(fmaps[:warm].contiguous(), boxes[:warm], classes[:warm], conf[:warm])
+    eager = runner._group(fmaps[:warm].contiguous(), boxes[:warm], classes[:warm], conf[:warm])
+    graph_equal = None
+    if a.graphs:                     # capture here (outside the timed region) and check the replay against the eager group
+        replay = runner._group_replayed(fmaps[:warm].contiguous(), boxes[:warm], classes[:warm], conf[:warm])
+        graph_equal = bool(torch.equal(replay[0], eager[0]) and torch.equal(replay[1], eager[1]))
 
     class View:                      # hands out contiguous groups of the expanded map without materialising the clip
         shape = fmaps.shape
@@ -87,7 +92,8 @@ def main():
         print(json.dumps({"workload": f"configs[4]: {a.frames}-frame clip, {a.det} detections -> {a.det * (a.det - 1)} pairs per "
                                       f"frame, pair build + vrd.forward + triplet top-100, all-gather of records",
                           "n_gpus": world, "frames": a.frames, "ms": float(ms.item()),
-                          "frames_per_s": a.frames / (float(ms.item()) * 1e-3), "records_ok": bool(ok), "association": assoc,
+                          "frames_per_s": a.frames / (float(ms.item()) * 1e-3), "records_ok": bool(ok), "graphs": a.graphs, "graph_replay_equals_eager": graph_equal,
+                          "association": assoc,
                           "gather_bytes": int(rec.numel() * 4)}), flush=True)
     if world > 1:
         dist.barrier()
