@@ -9,6 +9,8 @@
 // One launch builds everything a frame's pair list needs (indices, union boxes, 32x32 dual masks); one launch
 // selects the top-k triplets of a frame (radix select over the descending-order keys in shared-memory histograms,
 // ordered tie handling, bitonic sort of the winners, record gather).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace i2v {
@@ -83,24 +85,101 @@ __device__ __forceinline__ float topk_key_value(unsigned k) {
     return __uint_as_float(u);
 }
 
-// Single CTA.  keys[] (workspace, P*R uint32) holds the descending-order key of rel*conf_s*conf_o.
-__global__ void __launch_bounds__(kTopThreads) triplet_topk_kernel(
-    const float* __restrict__ rel_score, const float* __restrict__ conf, const int64_t* __restrict__ classes,
-    const float* __restrict__ boxes, const int64_t* __restrict__ ixs, const int64_t* __restrict__ ixo, int P, int R,
-    int top_k, unsigned* __restrict__ keys, float* __restrict__ record_out, int* __restrict__ count_out) {
-    __shared__ unsigned hist[2048];
-    __shared__ unsigned long long cand[kTopMax];
+// The selection runs in three launches:
+//   triplet_keys_kernel    (many CTAs) keys[i] = descending-order key of (rel * conf_s) * conf_o, and a histogram of the
+//                          keys' top 11 bits (shared-memory counts flushed with integer atomics: deterministic);
+//   triplet_filter_kernel  (many CTAs) finds the histogram bin d* in which the K-th best key lies and appends every
+//                          (key, flat index) whose top bits are <= d* to a candidate list (a few hundred to a few
+//                          thousand of the 532 K scores of a config-3 frame; list order is arbitrary);
+//   triplet_select_kernel  (one CTA) sorts the candidates as 64-bit (key << 32 | index) values -- best score first, ties
+//                          by lower flat index, whatever the list order -- and writes the K records.  If the list
+//                          overflowed (more than kCandCap keys share the threshold bin, e.g. all scores equal) it falls
+//                          back to a radix select over all keys.
+constexpr int kCandCap = 16384;
+constexpr int kHistBins = 2048;
+
+__global__ void __launch_bounds__(256) triplet_keys_kernel(const float* __restrict__ rel_score,
+                                                           const float* __restrict__ conf,
+                                                           const int64_t* __restrict__ ixs,
+                                                           const int64_t* __restrict__ ixo, int total, int R,
+                                                           unsigned* __restrict__ keys, unsigned* __restrict__ ghist) {
+    __shared__ unsigned hist[kHistBins];
+    for (int i = threadIdx.x; i < kHistBins; i += 256) hist[i] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int p = i / R;
+        // (rel * conf[ixs]) * conf[ixo], each product rounded to fp32 (lib/utils.py:611)
+        const float v = __fmul_rn(__fmul_rn(__ldg(rel_score + i), __ldg(conf + ixs[p])), __ldg(conf + ixo[p]));
+        const unsigned k = topk_desc_key(v);
+        keys[i] = k;
+        atomicAdd(&hist[k >> 21], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistBins; i += 256)
+        if (hist[i]) atomicAdd(ghist + i, hist[i]);
+}
+
+// the bin where the running count of the histogram reaches `need` (bins in ascending key order = best scores first)
+__device__ __forceinline__ unsigned threshold_bin(const unsigned* __restrict__ hist, unsigned need, int lane) {
+    constexpr int per = kHistBins / 32;
+    unsigned sum = 0;
+    for (int q = 0; q < per; ++q) sum += hist[lane * per + q];
+    unsigned incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned excl = incl - sum;
+    unsigned bin = kHistBins - 1;
+    if (excl < need && incl >= need) {
+        unsigned run = excl;
+        for (int q = 0; q < per; ++q) {
+            run += hist[lane * per + q];
+            if (run >= need) {
+                bin = lane * per + q;
+                break;
+            }
+        }
+    } else {
+        bin = 0xffffffffu;
+    }
+    const unsigned owner = __ballot_sync(0xffffffffu, bin != 0xffffffffu);
+    return owner ? __shfl_sync(0xffffffffu, bin, __ffs(owner) - 1) : kHistBins - 1;
+}
+
+__global__ void __launch_bounds__(256) triplet_filter_kernel(const unsigned* __restrict__ keys, int total, int K,
+                                                             const unsigned* __restrict__ ghist,
+                                                             unsigned* __restrict__ counter,
+                                                             unsigned long long* __restrict__ cand) {
+    __shared__ unsigned s_bin;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const unsigned b = threshold_bin(ghist, (unsigned)K, lane);
+        if (lane == 0) s_bin = b;
+    }
+    __syncthreads();
+    const unsigned dstar = s_bin;
+    const int n_iter = (total + gridDim.x * 256 - 1) / (gridDim.x * 256);
+    for (int it = 0; it < n_iter; ++it) {
+        const int i = (it * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        const unsigned k = i < total ? keys[i] : 0xffffffffu;
+        const bool take = i < total && (k >> 21) <= dstar;
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+            if (take && slot < (unsigned)kCandCap) cand[slot] = ((unsigned long long)k << 32) | (unsigned)i;
+        }
+    }
+}
+
+// Radix select over all keys by one CTA (the fallback of triplet_select_kernel): leaves the K winners in cand[0..K).
+__device__ void select_all_keys(const unsigned* __restrict__ keys, int total, int K, unsigned* hist,
+                                unsigned long long* cand) {
     __shared__ unsigned s_prefix, s_need, s_cnt, s_warp[32], s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = P * R;
-    const int K = min(top_k, total);
-
-    // keys: (rel * conf[ixs]) * conf[ixo], each product rounded to fp32 (lib/utils.py:611)
-    for (int i = tid; i < total; i += kTopThreads) {
-        int p = i / R;
-        float v = __fmul_rn(__fmul_rn(rel_score[i], __ldg(conf + ixs[p])), __ldg(conf + ixo[p]));
-        keys[i] = topk_desc_key(v);
-    }
     if (tid == 0) {
         s_prefix = 0;
         s_need = K;
@@ -189,10 +268,32 @@ __global__ void __launch_bounds__(kTopThreads) triplet_topk_kernel(
         }
     }
     __syncthreads();
-    // bitonic sort of the K winners by (key, index) ascending == (score descending, flat index ascending)
+}
+
+// One CTA.  cand_list / counter come from triplet_filter_kernel; dynamic shared memory: max(kCandCap, kTopMax) 64-bit slots.
+__global__ void __launch_bounds__(kTopThreads) triplet_select_kernel(
+    const int64_t* __restrict__ classes, const float* __restrict__ boxes, const int64_t* __restrict__ ixs,
+    const int64_t* __restrict__ ixo, int P, int R, int top_k, const unsigned* __restrict__ keys,
+    const unsigned* __restrict__ counter, const unsigned long long* __restrict__ cand_list,
+    float* __restrict__ record_out, int* __restrict__ count_out) {
+    extern __shared__ __align__(16) unsigned long long cand[];
+    __shared__ unsigned hist[kHistBins];
+    const int tid = threadIdx.x;
+    const int total = P * R;
+    const int K = min(top_k, total);
+    const unsigned M = K > 0 ? *counter : 0u;
+    int n_sort = K;
+    if (M > (unsigned)kCandCap) {
+        select_all_keys(keys, total, K, hist, cand);          // threshold bin too crowded: the slow, exact way
+    } else {
+        for (int i = tid; i < (int)M; i += kTopThreads) cand[i] = cand_list[i];
+        n_sort = (int)M;
+        __syncthreads();
+    }
+    // bitonic sort by (key, index) ascending == (score descending, flat index ascending); the first K are the winners
     int n2 = 1;
-    while (n2 < K) n2 <<= 1;
-    for (int i = K + tid; i < n2; i += kTopThreads) cand[i] = ~0ull;
+    while (n2 < n_sort) n2 <<= 1;
+    for (int i = n_sort + tid; i < n2; i += kTopThreads) cand[i] = ~0ull;
     __syncthreads();
     for (int size = 2; size <= n2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -251,9 +352,27 @@ extern "C" int i2v_pair_build(const float* boxes, int num_boxes, float im_h, flo
     return check_launch("pair_build_kernel");
 }
 
+struct TopkWs {
+    unsigned* keys;
+    unsigned* hist;             // [kHistBins] followed by the candidate counter
+    unsigned* counter;
+    unsigned long long* cand;   // [kCandCap]
+    size_t bytes;
+};
+static TopkWs carve_topk_ws(void* ws, int num_pairs, int num_rel) {
+    Carver cv(ws);
+    TopkWs w{};
+    w.keys = cv.take<unsigned>((size_t)num_pairs * num_rel);
+    w.hist = cv.take<unsigned>(kHistBins + 64);
+    w.counter = w.hist + kHistBins;
+    w.cand = cv.take<unsigned long long>(kCandCap);
+    w.bytes = cv.used();
+    return w;
+}
+
 extern "C" size_t i2v_triplet_topk_workspace_bytes(int num_pairs, int num_rel) {
     if (num_pairs < 0 || num_rel < 0) return 0;
-    return align_up((size_t)num_pairs * num_rel * sizeof(unsigned), 256);
+    return carve_topk_ws(nullptr, num_pairs, num_rel).bytes;
 }
 
 extern "C" int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
@@ -263,15 +382,25 @@ extern "C" int i2v_triplet_topk(const float* rel_score, const float* conf, const
     I2V_REQUIRE(num_pairs >= 0 && num_rel >= 0 && top_k >= 1 && top_k <= kTopMax, "triplet_topk: bad size (top_k <= %d)", kTopMax);
     I2V_REQUIRE((int64_t)num_pairs * num_rel <= INT32_MAX, "triplet_topk: too many scores");
     I2V_REQUIRE(record_out, "triplet_topk: null record_out");
-    size_t need = i2v_triplet_topk_workspace_bytes(num_pairs, num_rel);
-    if (need > 0) {
-        I2V_REQUIRE(rel_score && conf && classes && boxes && ixs && ixo, "triplet_topk: null pointer");
-        if (!workspace || workspace_bytes < need) {
-            set_error("triplet_topk: workspace %zu < %zu bytes", workspace_bytes, need);
-            return I2V_ERR_WORKSPACE;
-        }
+    const int total = num_pairs * num_rel;
+    const size_t need = i2v_triplet_topk_workspace_bytes(num_pairs, num_rel);
+    if (total > 0) I2V_REQUIRE(rel_score && conf && classes && boxes && ixs && ixo, "triplet_topk: null pointer");
+    if (!workspace || workspace_bytes < need) {
+        set_error("triplet_topk: workspace %zu < %zu bytes", workspace_bytes, need);
+        return I2V_ERR_WORKSPACE;
     }
-    triplet_topk_kernel<<<1, kTopThreads, 0, stream>>>(rel_score, conf, classes, boxes, ixs, ixo, num_pairs, num_rel,
-                                                       top_k, static_cast<unsigned*>(workspace), record_out, count_out);
-    return check_launch("triplet_topk_kernel");
+    const TopkWs w = carve_topk_ws(workspace, num_pairs, num_rel);
+    I2V_CUDA_TRY(cudaMemsetAsync(w.hist, 0, (kHistBins + 64) * sizeof(unsigned), stream));
+    if (total > 0) {
+        const int grid = (int)std::min<int64_t>(2 * kNumSMs, ((int64_t)total + 255) / 256);
+        triplet_keys_kernel<<<grid, 256, 0, stream>>>(rel_score, conf, ixs, ixo, total, num_rel, w.keys, w.hist);
+        I2V_TRY(check_launch("triplet_keys_kernel"));
+        triplet_filter_kernel<<<grid, 256, 0, stream>>>(w.keys, total, std::min(top_k, total), w.hist, w.counter, w.cand);
+        I2V_TRY(check_launch("triplet_filter_kernel"));
+    }
+    const size_t smem = (size_t)kCandCap * sizeof(unsigned long long);
+    I2V_CUDA_TRY(cudaFuncSetAttribute(triplet_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    triplet_select_kernel<<<1, kTopThreads, smem, stream>>>(classes, boxes, ixs, ixo, num_pairs, num_rel, top_k, w.keys,
+                                                           w.counter, w.cand, record_out, count_out);
+    return check_launch("triplet_select_kernel");
 }
