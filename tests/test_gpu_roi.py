@@ -367,3 +367,21 @@ def test_roi_align_properties_at_config2_size(ops, orc):
     phase = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase")
     assert float((phase - gin).abs().max()) <= 1e-5 * float(gin.abs().max())
     assert torch.equal(phase, ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase"))
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 60, 80), (2, 24, 38, 63)])   # planes too large for shared memory; C % 16 != 0
+def test_roi_align_backward_auto_falls_back_when_the_plane_kernels_cannot_run(ops, orc, shape):
+    """`auto` must pick a kernel that supports the shape (here: the gather kernel) and asking for a plane-resident kernel
+    explicitly must fail loudly instead of computing something else."""
+    from i2vsgg_b200._lib import I2VError
+    B, C, H, W = shape
+    feat = synth.feature_map(7, B, C, H, W)
+    rois = synth.rois(8, 40, batch=B)
+    rois[:, 1:] *= np.float32([W / 63.0, H / 38.0, W / 63.0, H / 38.0])
+    g = np.random.default_rng(6).standard_normal((40, C, 7, 7)).astype(np.float32)
+    want = orc.roi_align_pooled_backward(g, feat, rois, 7, 7, SCALE, "avg", nthreads=8)
+    got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat.shape, 7, 7, SCALE, "avg", "auto")
+    close(got, want)
+    for impl in ("phase", "plane", "rows"):
+        with pytest.raises(I2VError):
+            ops.roi_align_backward(cuda(g), None, cuda(rois), feat.shape, 7, 7, SCALE, "avg", impl)
