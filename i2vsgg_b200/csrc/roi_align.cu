@@ -745,6 +745,10 @@ bool bwd_rows_ok(const float* grad_out, int batch, int C, int H, int W, int PH, 
 int launch_bwd_rows(const float* grad_out, const LatticeRoi* tab, void* rtab_space, const int* order, const int* starts,
                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 
+// roi_align_fwd_slab.cu: the forward on planes brought in by one bulk copy
+bool fwd_slab_ok(const float* features, const float* out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
+int launch_fwd_slab(const float* feat, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts, float* out,
+                    int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 // roi_align_bwd_phase.cu: the phased backward (warp = lattice row, CTA barrier between feature-row phases)
 size_t bwd_phase_smem_bytes(int H, int W);
 bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
@@ -912,6 +916,15 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
         set_error("roi_align_forward: the plane kernel needs a 7x7 output, C %% 16 == 0, a 16-byte aligned output and "
                   "16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
+    }
+    // AUTO prefers the slab kernel (one TMA bulk copy fills the planes; 16 warps, one RoI each) where its bank argument
+    // holds; `impl = plane` keeps the cell-major plane kernel, which also serves the other shapes and the max pool
+    if (impl == I2V_IMPL_AUTO &&
+        fwd_slab_ok(features, out, batch, channels, height, width, pooled_h, pooled_w, pool_mode)) {
+        I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        return launch_fwd_slab(features, w.tab, w.ptab, w.order, w.starts, out, batch, channels, height, width, num_rois,
+                               pool_mode, stream);
     }
     bool plane = can_plane && impl != I2V_IMPL_GATHER;
     I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, plane, w));
