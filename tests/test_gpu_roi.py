@@ -385,3 +385,41 @@ def test_roi_align_backward_auto_falls_back_when_the_plane_kernels_cannot_run(op
     for impl in ("phase", "plane", "rows"):
         with pytest.raises(I2VError):
             ops.roi_align_backward(cuda(g), None, cuda(rois), feat.shape, 7, 7, SCALE, "avg", impl)
+
+
+def test_roi_align_kernels_agree_on_random_shapes(ops):
+    """Forty random (frames, channels, map, RoI) configurations -- tiny and huge boxes, boxes over the border, stray frame
+    indices, maps of every aspect ratio that fits shared memory: every plane-resident backward kernel a shape supports must
+    agree with the gather kernel (the reference's atomic scatter) to 2e-5 of scale and be bit-reproducible, and the forward
+    that `auto` picks must agree with the gather forward."""
+    from i2vsgg_b200._lib import I2VError
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for trial in range(40):
+        B = int(rng.integers(1, 4)); C = 16 * int(rng.integers(1, 4))
+        H = int(rng.integers(2, 48)); W = int(rng.integers(2, 70))
+        if H * W * 64 + 80000 > 232448:
+            continue
+        N = int(rng.integers(1, 120))
+        iw, ih = W * 16.0, H * 16.0
+        x1 = rng.uniform(-30, iw, N); y1 = rng.uniform(-30, ih, N)
+        w = rng.choice([1.0, 6.0, 20.0, 60.0, 200.0, 700.0], N); h = rng.choice([1.0, 6.0, 20.0, 60.0, 200.0, 700.0], N)
+        rois = cuda(np.stack([rng.integers(-1, B + 1, N), x1, y1, x1 + w, y1 + h], 1).astype(np.float32))
+        gen = torch.Generator(device="cuda").manual_seed(trial)
+        g = torch.randn((N, C, 7, 7), device="cuda", generator=gen)
+        feat = torch.randn((B, C, H, W), device="cuda", generator=gen)
+        for pool in ("avg", "none"):
+            ref = ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, "gather")
+            scale = max(float(ref.abs().max()), 1e-6)
+            for impl in ("phase", "plane", "rows"):
+                try:
+                    out = ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, impl)
+                except I2VError:
+                    continue                     # the shape is outside what this kernel takes
+                assert float((out - ref).abs().max()) <= 2e-5 * scale, (trial, B, C, H, W, N, pool, impl)
+                assert torch.equal(out, ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, impl))
+                checked += 1
+            fref = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, "gather")
+            fout = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, "auto")
+            assert float((fout - fref).abs().max()) <= 2e-5 * max(float(fref.abs().max()), 1e-6), (trial, H, W, pool)
+    assert checked >= 100
