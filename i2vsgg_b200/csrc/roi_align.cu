@@ -12,6 +12,8 @@
 //           conflict free and all index math is warp-uniform; pooled tiles leave through TMA bulk stores;
 //   gather  one thread per output element straight from global memory (any shape; fp64 weights like the
 //           reference, so its forward is bit-identical to roi_align.c).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace i2v {
@@ -755,6 +757,13 @@ bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH,
 int launch_bwd_phase(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
                      float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 
+// roi_align_bwd_band.cu: the band-owner backward (lanes = 32 channels, a CTA owns a slab of feature rows, a warp a band)
+bool bwd_band_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
+size_t bwd_band_list_ints(int batch, int num_rois);
+int launch_bwd_band(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
+                    int* lists, float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, int bands,
+                    cudaStream_t stream);
+
 struct LatticeWs {
     LatticeRoi* tab;
     PlaneTab* ptab;   // the plane tables share one allocation: the forward view or the backward view of a call
@@ -763,6 +772,7 @@ struct LatticeWs {
     int* counts;
     int* starts;
     int* order;
+    int* band_lists;  // per-(frame, slab) RoI lists of the band-owner backward
     size_t bytes;
 };
 
@@ -780,6 +790,7 @@ static LatticeWs carve_lattice_ws(void* ws, int batch, int num_rois, bool lists 
         // RowTab / PhaseTab of roi_align_bwd_rows.cu / roi_align_bwd_phase.cu)
         w.ptab = reinterpret_cast<PlaneTab*>(cv.take<unsigned char>((size_t)num_rois * kRoiTabSlotBytes));
         w.btab = reinterpret_cast<BwdTab*>(w.ptab);
+        w.band_lists = cv.take<int>(bwd_band_list_ints(batch, num_rois));
         static_assert(sizeof(BwdTab) <= kRoiTabSlotBytes && sizeof(PlaneTab) <= kRoiTabSlotBytes, "table slot");
     }
     w.bytes = cv.used();
@@ -880,7 +891,7 @@ static int roi_align_check(const char* who, const void* a, const void* b, const 
                            int& GH, int& GW) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0, "%s: negative size", who);
     I2V_REQUIRE(pool_mode >= I2V_POOL_NONE && pool_mode <= I2V_POOL_MAX, "%s: bad pool_mode %d", who, pool_mode);
-    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_PHASE, "%s: bad impl %d", who, impl);
+    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_BAND, "%s: bad impl %d", who, impl);
     GH = pooled_h + (pool_mode != I2V_POOL_NONE);
     GW = pooled_w + (pool_mode != I2V_POOL_NONE);
     I2V_REQUIRE(pooled_h >= 1 && pooled_w >= 1 && GH >= 2 && GW >= 2 && GH <= kMaxLattice && GW <= kMaxLattice,
@@ -965,13 +976,26 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                     bwd_rows_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     bool can_phase = zero_first && num_rois > 0 &&
                      bwd_phase_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    bool can_band = zero_first && num_rois > 0 &&
+                    bwd_band_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows) ||
-        (impl == I2V_IMPL_PHASE && !can_phase)) {
+        (impl == I2V_IMPL_PHASE && !can_phase) || (impl == I2V_IMPL_BAND && !can_band)) {
         set_error("roi_align_backward: the plane kernels need a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
                   "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
     }
-    // AUTO takes the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
+    // AUTO takes the band-owner kernel (roi_align_bwd_band.cu) where 32 channels divide C; then the phased kernel
+    if (can_band && (impl == I2V_IMPL_BAND || impl == I2V_IMPL_AUTO)) {
+        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        static const int bands = [] {
+            const char* e = getenv("I2V_BAND_WARPS");
+            return e ? atoi(e) : 0;
+        }();
+        return launch_bwd_band(grad_out, w.tab, w.ptab, w.order, w.starts, w.band_lists, grad_in, batch, channels, height,
+                               width, num_rois, pool_mode, bands, stream);
+    }
+    // the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
     // 2.35 ms for the row-owner kernel (profiles/README.md); the other two stay selectable and serve as cross-checks
     if (can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO)) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));

@@ -80,6 +80,8 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
                               construction; forward treats it like I2V_IMPL_PLANE)                                 */
 #define I2V_IMPL_PHASE 4   /* backward only: plane-resident, warp = lattice row, lanes = (cell of the bilinear pair,
                               channel); conflict-free, CTA barrier between feature-row phases (forward: like PLANE)    */
+#define I2V_IMPL_BAND 5    /* backward only: lanes = 32 channels, a CTA owns a slab of feature rows of (frame, 32
+                              channels), each warp a band of those rows: no ordering between warps (forward: like PLANE) */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.

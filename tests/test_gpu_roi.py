@@ -95,12 +95,14 @@ def test_roi_align_empty(ops):
 
 
 @pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "phase", "auto"])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "phase", "band", "auto"])
+@pytest.mark.parametrize("case", CASES + [(2, 64, 38, 63, 80)])
 def test_roi_align_backward(ops, orc, case, impl, pool):
-    if impl in ("plane", "rows", "phase") and pool == "max":
+    if impl in ("plane", "rows", "phase", "band") and pool == "max":
         pytest.skip("the max pool's arg-max routing needs the features: gather kernel only")
     B, C, H, W, N = case
+    if impl == "band" and C % 32:
+        pytest.skip("the band-owner kernel takes 32 channels per CTA")
     feat = synth.feature_map(100 + B, B, C, H, W)
     rois = synth.rois(200 + N, N, batch=B)
     if W != 63:
@@ -115,7 +117,7 @@ def test_roi_align_backward_small_and_repeated_cells(ops, orc):
     # tiny RoIs (several lattice points per cell in both axes), RoIs hugging the borders and many RoIs stacked on the
     # same cells: exercises the run-position serialisation and the column merge of the plane kernel
     rng = np.random.default_rng(17)
-    B, C, H, W, N = 2, 16, 38, 63, 120
+    B, C, H, W, N = 2, 32, 38, 63, 120
     feat_shape = (B, C, H, W)
     x1 = rng.uniform(0, 980, N); y1 = rng.uniform(0, 580, N)
     w = rng.choice([2.0, 9.0, 20.0, 45.0, 70.0, 130.0], N); h = rng.choice([2.0, 9.0, 20.0, 45.0, 70.0, 130.0], N)
@@ -126,7 +128,7 @@ def test_roi_align_backward_small_and_repeated_cells(ops, orc):
     for pool in ("avg", "none"):
         want = orc.roi_align_pooled_backward(g, None if pool != "max" else None, rois, 7, 7, SCALE, pool) \
             if False else orc.roi_align_pooled_backward(g, np.zeros(feat_shape, np.float32), rois, 7, 7, SCALE, pool)
-        for impl in ("plane", "rows", "phase"):
+        for impl in ("plane", "rows", "phase", "band"):
             got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
             close(got, want)
             again = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
@@ -367,6 +369,15 @@ def test_roi_align_properties_at_config2_size(ops, orc):
     phase = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase")
     assert float((phase - gin).abs().max()) <= 1e-5 * float(gin.abs().max())
     assert torch.equal(phase, ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", "phase"))
+    del phase
+    # the kernel `auto` picks (band-owner): against the plane kernel, bit-reproducible, and the adjoint identity again
+    for impl in ("band", "auto"):
+        band = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", impl)
+        assert float((band - gin).abs().max()) <= 1e-5 * float(gin.abs().max())
+        assert torch.equal(band, ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "avg", impl))
+        rhs = float((feat.double() * band.double()).sum())
+        assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), float((out.double().abs() * grad.double().abs()).sum()) * 1e-2)
+        del band
 
 
 @pytest.mark.parametrize("shape", [(1, 16, 60, 80), (2, 24, 38, 63)])   # planes too large for shared memory; C % 16 != 0
@@ -411,7 +422,7 @@ def test_roi_align_kernels_agree_on_random_shapes(ops):
         for pool in ("avg", "none"):
             ref = ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, "gather")
             scale = max(float(ref.abs().max()), 1e-6)
-            for impl in ("phase", "plane", "rows"):
+            for impl in ("phase", "plane", "rows", "band"):
                 try:
                     out = ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, impl)
                 except I2VError:
