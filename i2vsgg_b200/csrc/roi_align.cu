@@ -984,7 +984,16 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                   "aligned gradient and 16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
     }
-    // AUTO takes the band-owner kernel (roi_align_bwd_band.cu) where 32 channels divide C; then the phased kernel
+    // AUTO takes the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
+    // 2.35 ms for the row-owner kernel (profiles/README.md); the other two stay selectable and serve as cross-checks
+    if (can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO)) {
+        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
+                                num_rois, pool_mode, stream);
+    }
+    // the band-owner kernel (roi_align_bwd_band.cu) keeps maps of any size plane-resident (a CTA owns a slab of rows):
+    // AUTO takes it where the phased kernel cannot hold 16 whole planes (1.7 ms against 1.49 ms on config 2 otherwise)
     if (can_band && (impl == I2V_IMPL_BAND || impl == I2V_IMPL_AUTO)) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
@@ -994,14 +1003,6 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
         }();
         return launch_bwd_band(grad_out, w.tab, w.ptab, w.order, w.starts, w.band_lists, grad_in, batch, channels, height,
                                width, num_rois, pool_mode, bands, stream);
-    }
-    // the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
-    // 2.35 ms for the row-owner kernel (profiles/README.md); the other two stay selectable and serve as cross-checks
-    if (can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO)) {
-        I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
-        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
-        return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
-                                num_rois, pool_mode, stream);
     }
     if (can_rows && (impl == I2V_IMPL_ROWS || (impl == I2V_IMPL_AUTO && !can_plane))) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));

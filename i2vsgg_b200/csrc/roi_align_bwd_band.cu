@@ -22,6 +22,8 @@
 //   * lattice columns two apart never share a cell unless the RoI is narrower than a cell per bin, so the eight columns
 //     of a feature row go as two static passes (even, odd) of hoisted loads / FFMA2 / stores; the rare narrow RoIs take
 //     a column-by-column path.  Columns off the map point at two padding cells behind every plane row with weight zero.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace i2v {
@@ -314,14 +316,17 @@ __device__ __forceinline__ void lattice_row(const unsigned (&a)[8], const unsign
 
 // WPT: plane row pitch in cells (W + 2) as a compile-time constant, so that the lower row of a lattice row is an
 // immediate offset; 0: any width (the two rows are then handled one after the other)
+constexpr int kProducers = 4;       // producer warps: one thread each walks every kProducers-th RoI of the list (the
+                                    // wait / expect / two bulk copies of one RoI take a thread ~450 cycles)
+
 template <int POOL, int NB, int WPT>
-__global__ void __launch_bounds__((NB + 1) * 32, 1)
+__global__ void __launch_bounds__((NB + kProducers) * 32, 1)
     lattice_bwd_band_kernel(const float* __restrict__ grad_out, const unsigned char* __restrict__ tab_space,
                             const int* __restrict__ sorder, const int* __restrict__ scount, const int* __restrict__ starts,
                             const int* __restrict__ bounds, float* __restrict__ grad_in, int C, int H, int Wrt, int nslabs,
-                            int slab_rows, int stages, int num_rois) {
+                            int slab_rows, int stages, int num_rois, int debug) {
     constexpr int P = 7;
-    constexpr int kThreads = (NB + 1) * 32;
+    constexpr int kThreads = (NB + kProducers) * 32;
     const int W = WPT ? WPT - 2 : Wrt;
     const int WP = W + 2;                                    // two padding cells behind every plane row
     const int RB = WP * 128;                                 // plane row pitch in bytes
@@ -355,13 +360,16 @@ __global__ void __launch_bounds__((NB + 1) * 32, 1)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    if (warp == NB) {
-        // ---- producer: the warp reads the slab's RoI list 32 entries at a time; lane 0 walks the ring ----
-        int st = 0;
-        unsigned round = 0;
-        for (int base = 0; base < count; base += 32) {
-            const int mine = (base + lane < count) ? __ldg(list + base + lane) : 0;
-            const int lim = min(32, count - base);
+    if (warp >= NB) {
+        // ---- producers: warp NB + p takes the list entries k = p (mod kProducers); it reads 32 of them at a time and
+        // lane 0 issues the two bulk copies of each (slot k % stages, in use for the (k / stages)-th time) ----
+        const int pw = warp - NB;
+        int st = pw % stages;
+        unsigned round = pw / stages;
+        for (int base = pw; base < count; base += 32 * kProducers) {
+            const int idx = base + lane * kProducers;
+            const int mine = idx < count ? __ldg(list + idx) : 0;
+            const int lim = min(32, (count - base + kProducers - 1) / kProducers);
             for (int i = 0; i < lim; ++i) {
                 const int n = __shfl_sync(0xffffffffu, mine, i);
                 if (lane == 0) {
@@ -371,8 +379,9 @@ __global__ void __launch_bounds__((NB + 1) * 32, 1)
                     bulk_load(dst, grad_out + ((size_t)n * C + (size_t)ct * kK) * 49, kTileBytes, full + st * 8);
                     bulk_load(dst + kTileBytes, tab_space + (size_t)n * kRoiTabSlotBytes, kTabBytes, full + st * 8);
                 }
-                if (++st == stages) {
-                    st = 0;
+                st += kProducers;
+                while (st >= stages) {
+                    st -= stages;
                     ++round;
                 }
                 __syncwarp();
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__((NB + 1) * 32, 1)
             // lanes 0-7 test one lattice row each
             const unsigned ysl = lds_u8(t + 144 + (lane & 7));
             unsigned bits = __ballot_sync(0xffffffffu, ysl >= ylo && ysl <= yhi) & 0xffu;
-            if (idle) bits = 0;
+            if (idle || debug == 1) bits = 0;
             if (bits) {
                 const uint4 hdr = lds_u4(t + 144);                  // {ys[0..3], ys[4..7], xmode, rows}
                 const uint4 xo = lds_u4(t + 128);
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__((NB + 1) * 32, 1)
         const size_t HW = (size_t)H * W;
         float* dst = grad_in + ((size_t)b * C + (size_t)ct * kK + (size_t)q * 4) * HW + (size_t)s0 * W;
         const float4* src = reinterpret_cast<const float4*>(planes);
-        for (int r = warp; r < nrows; r += NB + 1) {
+        for (int r = warp; r < nrows; r += NB + kProducers) {
             for (int x = sub; x < W; x += 4) {
                 const float4 v = src[(r * WP + x) * (kK / 4) + q];
                 float* p = dst + (size_t)r * W + x;
@@ -538,8 +547,9 @@ static int launch_band(const float* grad_out, const unsigned char* tab_space, co
     auto kern = lattice_bwd_band_kernel<POOL, NB, WPT>;
     const size_t smem = (size_t)stages * kStageBytes + kBarBytes + (size_t)slab_rows * (W + 2) * kK * sizeof(float);
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)(batch * (C / kK) * nslabs)), (NB + 1) * 32, smem, stream>>>(
-        grad_out, tab_space, sorder, scount, starts, bounds, grad_in, C, H, W, nslabs, slab_rows, stages, num_rois);
+    kern<<<dim3((unsigned)(batch * (C / kK) * nslabs)), (NB + kProducers) * 32, smem, stream>>>(
+        grad_out, tab_space, sorder, scount, starts, bounds, grad_in, C, H, W, nslabs, slab_rows, stages, num_rois,
+        getenv("I2V_BAND_DEBUG") ? atoi(getenv("I2V_BAND_DEBUG")) : 0);
     return check_launch("lattice_bwd_band_kernel");
 }
 template <int POOL, int NB>
@@ -553,7 +563,7 @@ static int launch_band_w(const float* grad_out, const unsigned char* tab_space, 
                                     slab_rows, stages, num_rois, stream);
 }
 
-constexpr int kBandDefaultWarps = 8;
+constexpr int kBandDefaultWarps = 12;
 
 // `tab` holds the LatticeRoi tables of this call; `tab_space` is the workspace's per-RoI table slot (kRoiTabSlotBytes
 // each); `lists` has room for bwd_band_list_ints(batch, num_rois) ints.  `bands` (4, 8, 12 or 16; 0 = default) is the

@@ -398,6 +398,22 @@ def test_roi_align_backward_auto_falls_back_when_the_plane_kernels_cannot_run(op
             ops.roi_align_backward(cuda(g), None, cuda(rois), feat.shape, 7, 7, SCALE, "avg", impl)
 
 
+def test_roi_align_backward_large_map_stays_plane_resident(ops, orc):
+    """A 60x80 map (16 planes = 307 KB) does not fit the phased kernel; with C % 32 == 0 `auto` takes the band-owner
+    kernel, which cuts the map into slabs of rows (here four) -- against the oracle, and bit-reproducible."""
+    B, C, H, W, N = 2, 32, 60, 80, 70
+    feat_shape = (B, C, H, W)
+    rois = synth.rois(31, N, batch=B)
+    rois[:, 1:] *= np.float32([W / 63.0, H / 38.0, W / 63.0, H / 38.0])
+    g = np.random.default_rng(8).standard_normal((N, C, 7, 7)).astype(np.float32)
+    for pool in ("avg", "none"):
+        want = orc.roi_align_pooled_backward(g, np.zeros(feat_shape, np.float32), rois, 7, 7, SCALE, pool, nthreads=8)
+        for impl in ("band", "auto"):
+            got = ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl)
+            close(got, want)
+            assert torch.equal(got, ops.roi_align_backward(cuda(g), None, cuda(rois), feat_shape, 7, 7, SCALE, pool, impl))
+
+
 def test_roi_align_kernels_agree_on_random_shapes(ops):
     """Forty random (frames, channels, map, RoI) configurations -- tiny and huge boxes, boxes over the border, stray frame
     indices, maps of every aspect ratio that fits shared memory: every plane-resident backward kernel a shape supports must
