@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libi2vsgg_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
-IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, IMPL_ROWS, IMPL_PHASE, IMPL_BAND = 0, 1, 2, 3, 4, 5
+IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, IMPL_ROWS, IMPL_PHASE, IMPL_BAND, IMPL_SLAB = 0, 1, 2, 3, 4, 5, 6
 ARGMAX_FLAT, ARGMAX_PLANE = 0, 1
 DT_F32, DT_BF16, DT_TF32 = 0, 1, 2
 
@@ -44,7 +44,10 @@ SIGNATURES = {
     "i2v_rpn_cls_prob": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "i2v_proposal_stages": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "i2v_pair_build": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "i2v_pair_build_frames": (_i, [_vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "i2v_triplet_topk_workspace_bytes": (_sz, [_i, _i]),
+    "i2v_triplet_topk_frames_workspace_bytes": (_sz, [_i, _i, _i]),
+    "i2v_triplet_topk_frames": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "i2v_triplet_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "i2v_roi_pool_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _ll, _i, _vp]),
     "i2v_linear_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _vp]),

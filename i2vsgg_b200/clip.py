@@ -47,36 +47,27 @@ class ClipRunner:
         return out[0].clone(), out[1].clone()
 
     def _group(self, fmap, boxes, classes, conf):
-        """fmap [F,C,H,W], boxes [F,N,4], classes [F,N], conf [F,N] (device) -> records [F,top_k,13], counts [F]."""
+        """fmap [F,C,H,W], boxes [F,N,4], classes [F,N], conf [F,N] (device) -> records [F,top_k,13], counts [F].
+
+        No per-frame Python loop: ONE launch builds the pair lists, union boxes and object masks of the whole group
+        (`ops.pair_build_frames`; the [P,2,32,32] pair masks of faster_rcnn_SGG_emb.py:654-655 are never written, the head
+        takes one mask per object), the relation head runs once over the group's rows, and three launches select the top
+        triplets of all frames (`ops.triplet_topk_frames`)."""
         F, N = boxes.shape[:2]
         dev = fmap.device
         P = N * (N - 1)
         rep1, inv1 = sgg.unordered_pairs(N, dev)
         U = rep1.numel()
-        ixs_l, ixo_l, rel_l, mask_l = [], [], [], []
-        first = torch.arange(N, device=dev) * (N - 1)               # the first pair whose subject is object i
-        for f in range(F):
-            ixs, ixo, rel, masks = sgg.build_pairs(boxes[f], self.im_h, self.im_w, device=dev)
-            rel[:, 0] = float(f)                                     # RoI rows carry the frame index of the group
-            ixs_l.append(ixs + f * N)
-            ixo_l.append(ixo + f * N)
-            rel_l.append(rel)
-            mask_l.append(masks[first, 0])                           # the N object masks (channel 0 = subject)
+        boxes = boxes.contiguous()
+        ixs, ixo, rel, obj_masks = ops.pair_build_frames(boxes, self.im_h, self.im_w)
         rois = torch.cat([torch.arange(F, device=dev, dtype=torch.float32).repeat_interleave(N)[:, None],
                           boxes.reshape(F * N, 4)], 1)
         offs = torch.arange(F, device=dev)
         rep = (rep1[None, :] + offs[:, None] * P).reshape(-1)
         inv = (inv1[None, :] + offs[:, None] * U).reshape(-1)
-        ixs, ixo = torch.cat(ixs_l), torch.cat(ixo_l)
-        scores, _ = self.head(fmap, rois, torch.cat(rel_l), None, None, ixs, ixo, return_numpy=False,
-                              rel_unique=(rep, inv), obj_masks=torch.cat(mask_l))
-        rec = torch.empty((F, self.top_k, shard.RECORD_WIDTH), dtype=torch.float32, device=dev)
-        cnt = torch.empty((F,), dtype=torch.int32, device=dev)
-        for f in range(F):
-            r, c = ops.triplet_topk(scores[f * P:(f + 1) * P], conf[f], classes[f], boxes[f], ixs_l[f] - f * N,
-                                    ixo_l[f] - f * N, self.top_k)
-            rec[f], cnt[f] = r, c[0]
-        return rec, cnt
+        scores, _ = self.head(fmap, rois, rel, None, None, ixs, ixo, return_numpy=False, rel_unique=(rep, inv),
+                              obj_masks=obj_masks)
+        return ops.triplet_topk_frames(scores, conf, classes, boxes, ixs[:P], ixo[:P], self.top_k)
 
     def run(self, fmaps, boxes, classes, conf, num_frames: int, rank: int = 0, world: int = 1, group=None):
         """This rank's frames (`fmaps` [f,C,H,W], `boxes` [f,N,4], `classes` [f,N], `conf` [f,N], in clip order)

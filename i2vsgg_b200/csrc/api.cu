@@ -1,10 +1,12 @@
 // Error reporting, ABI version and the five drop-in launchers that keep the reference's names and argument
 // lists (lib/model/roi_align/src/roi_align_kernel.h:13-27, lib/model/roi_pooling/src/roi_pooling_kernel.h:8-18,
 // lib/model/nms/src/nms_cuda_kernel.h:5-6).  The launchers have no workspace argument, so they keep one grow-only
-// device buffer per (thread, device); everything else in the library takes the caller's workspace.
+// device buffer per (thread, device, stream); everything else in the library takes the caller's workspace.
 #include <limits.h>
 #include <stdarg.h>
 #include <string.h>
+
+#include <utility>
 
 #include "common.cuh"
 
@@ -23,34 +25,57 @@ struct Scratch {
     void* ptr = nullptr;
     size_t bytes = 0;
     int device = -1;
+    cudaStream_t stream = nullptr;
 };
-static thread_local Scratch g_scratch;
+constexpr int kMaxScratch = 16;
+static thread_local Scratch g_scratch[kMaxScratch];
+static thread_local int g_scratch_used = 0;
 
-// Grow-only scratch for the legacy launchers.  Growing synchronises the device (the old buffer may still be in
-// use by work queued on another stream), which happens a handful of times per process.
-void* legacy_scratch(size_t bytes, size_t* have) {
+// Grow-only scratch for the legacy launchers, one buffer per (thread, device, stream): two launcher calls of one thread
+// on different streams never share tables, like the stateless reference launchers.  Growing a buffer waits for the work
+// queued on its stream (the old buffer may still be in use there), which happens a handful of times per process.  With
+// more than kMaxScratch live (device, stream) pairs in one thread the oldest entry is recycled the same way.
+void* legacy_scratch(size_t bytes, size_t* have, cudaStream_t stream) {
     int dev = 0;
     if (have) *have = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (g_scratch.ptr && g_scratch.device == dev && g_scratch.bytes >= bytes) {
-        if (have) *have = g_scratch.bytes;
-        return g_scratch.ptr;
+    Scratch* e = nullptr;
+    for (int i = 0; i < g_scratch_used; ++i)
+        if (g_scratch[i].device == dev && g_scratch[i].stream == stream) e = &g_scratch[i];
+    if (e && e->bytes >= bytes) {
+        if (have) *have = e->bytes;
+        return e->ptr;
     }
-    if (g_scratch.ptr && g_scratch.device == dev) {
-        cudaDeviceSynchronize();
-        cudaFree(g_scratch.ptr);
+    if (!e) {
+        if (g_scratch_used < kMaxScratch) {
+            e = &g_scratch[g_scratch_used++];
+        } else {
+            e = &g_scratch[0];
+            for (int i = 1; i < kMaxScratch; ++i) std::swap(g_scratch[i - 1], g_scratch[i]);   // recycle the oldest
+            e = &g_scratch[kMaxScratch - 1];
+        }
     }
-    g_scratch = Scratch{};
+    if (e->ptr) {
+        int cur = dev;
+        if (e->device != dev) cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+        cudaFree(e->ptr);
+        if (e->device != cur) cudaSetDevice(cur);
+        cudaGetLastError();
+    }
+    *e = Scratch{};
     size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 2;
     void* p = nullptr;
     if (cudaMalloc(&p, want) != cudaSuccess) {
         set_error("legacy launcher: cudaMalloc(%zu) failed", want);
         cudaGetLastError();
+        e->device = -1;
         return nullptr;
     }
-    g_scratch.ptr = p;
-    g_scratch.bytes = want;
-    g_scratch.device = dev;
+    e->ptr = p;
+    e->bytes = want;
+    e->device = dev;
+    e->stream = stream;
     if (have) *have = want;
     return p;
 }
@@ -96,7 +121,7 @@ extern "C" void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host,
     size_t box_bytes = align_up((size_t)boxes_num * boxes_dim * sizeof(float), 256);
     size_t need = box_bytes + i2v_nms_workspace_bytes(1, boxes_num);
     size_t have = 0;
-    char* ws = static_cast<char*>(legacy_scratch(need, &have));
+    char* ws = static_cast<char*>(legacy_scratch(need, &have, nullptr));
     if (!ws) return;
     const float* dev_boxes = boxes_host;
     cudaPointerAttributes attr;

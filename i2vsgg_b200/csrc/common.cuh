@@ -11,9 +11,9 @@ namespace i2v {
 // Records a human-readable message for i2v_last_error(); thread-local.
 void set_error(const char* fmt, ...);
 
-// Grow-only per-(thread, device) device buffer for the reference-signature launchers, which have no workspace
+// Grow-only per-(thread, device, stream) device buffer for the reference-signature launchers, which have no workspace
 // argument.  Returns nullptr (and sets the error) when the allocation fails; *have receives the buffer size.
-void* legacy_scratch(size_t bytes, size_t* have);
+void* legacy_scratch(size_t bytes, size_t* have, cudaStream_t stream);
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

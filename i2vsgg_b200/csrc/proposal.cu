@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
     float* narea = carea + kNmsThreads;                          // [2][32]
     __shared__ int s_nk;
     __shared__ int s_ncnt[2];
+    __shared__ int s_nkv[2];   // the running count as published in turn w (double-buffered like s_ncnt: warp w + 1 may
+                               // already be writing s_nk for its own turn while slower warps still test turn w's value)
 
     const int set = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -375,11 +377,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
                 }
                 if (lane == 0) {
                     s_ncnt[pb] = cnt;
+                    s_nkv[pb] = nk + cnt;
                     s_nk = nk + cnt;
                 }
             }
             __syncthreads();
-            if (s_nk >= limit) {
+            if (s_nkv[pb] >= limit) {
                 done = true;
                 break;
             }

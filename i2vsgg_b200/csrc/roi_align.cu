@@ -755,7 +755,8 @@ int launch_fwd_slab(const float* feat, const LatticeRoi* tab, void* tab_space, c
 size_t bwd_phase_smem_bytes(int H, int W);
 bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
 int launch_bwd_phase(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
-                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
+                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, int accumulate,
+                     cudaStream_t stream);
 
 // roi_align_bwd_band.cu: the band-owner backward (lanes = 32 channels, a CTA owns a slab of feature rows, a warp a band)
 bool bwd_band_ok(const float* grad_out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
@@ -891,7 +892,7 @@ static int roi_align_check(const char* who, const void* a, const void* b, const 
                            int& GH, int& GW) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0, "%s: negative size", who);
     I2V_REQUIRE(pool_mode >= I2V_POOL_NONE && pool_mode <= I2V_POOL_MAX, "%s: bad pool_mode %d", who, pool_mode);
-    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_BAND, "%s: bad impl %d", who, impl);
+    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_SLAB, "%s: bad impl %d", who, impl);
     GH = pooled_h + (pool_mode != I2V_POOL_NONE);
     GW = pooled_w + (pool_mode != I2V_POOL_NONE);
     I2V_REQUIRE(pooled_h >= 1 && pooled_w >= 1 && GH >= 2 && GW >= 2 && GH <= kMaxLattice && GW <= kMaxLattice,
@@ -923,15 +924,20 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
                             pooled_h, pooled_w, pool_mode, impl, GH, GW));
     if (num_rois == 0 || channels == 0) return I2V_OK;
     bool can_plane = plane_forward_ok(out, batch, channels, height, width, pooled_h, pooled_w);
-    if (impl >= I2V_IMPL_PLANE && !can_plane) {
+    const bool can_slab = fwd_slab_ok(features, out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    if (impl == I2V_IMPL_SLAB && !can_slab) {
+        set_error("roi_align_forward: the slab kernel needs a 7x7 output, pool none/avg, C %% 16 == 0, H*W = 2 (mod 4) and 16 "
+                  "planes that fit shared memory");
+        return I2V_ERR_UNSUPPORTED;
+    }
+    if (impl >= I2V_IMPL_PLANE && impl != I2V_IMPL_SLAB && !can_plane) {
         set_error("roi_align_forward: the plane kernel needs a 7x7 output, C %% 16 == 0, a 16-byte aligned output and "
                   "16 planes that fit shared memory");
         return I2V_ERR_UNSUPPORTED;
     }
     // AUTO prefers the slab kernel (one TMA bulk copy fills the planes; 16 warps, one RoI each) where its bank argument
     // holds; `impl = plane` keeps the cell-major plane kernel, which also serves the other shapes and the max pool
-    if (impl == I2V_IMPL_AUTO &&
-        fwd_slab_ok(features, out, batch, channels, height, width, pooled_h, pooled_w, pool_mode)) {
+    if ((impl == I2V_IMPL_AUTO || impl == I2V_IMPL_SLAB) && can_slab) {
         I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
         return launch_fwd_slab(features, w.tab, w.ptab, w.order, w.starts, out, batch, channels, height, width, num_rois,
@@ -974,10 +980,14 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                      plane_backward_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     bool can_rows = zero_first && num_rois > 0 &&
                     bwd_rows_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
-    bool can_phase = zero_first && num_rois > 0 &&
-                     bwd_phase_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    // the phased kernel can also ADD its planes to grad_in (the reference launcher's contract)
+    bool can_phase = num_rois > 0 && bwd_phase_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     bool can_band = zero_first && num_rois > 0 &&
                     bwd_band_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
+    if (impl == I2V_IMPL_SLAB) {
+        set_error("roi_align_backward: I2V_IMPL_SLAB is a forward kernel");
+        return I2V_ERR_UNSUPPORTED;
+    }
     if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows) ||
         (impl == I2V_IMPL_PHASE && !can_phase) || (impl == I2V_IMPL_BAND && !can_band)) {
         set_error("roi_align_backward: the plane kernels need a 7x7 pooled size, pool none/avg, C %% 16 == 0, a 16-byte "
@@ -990,7 +1000,7 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
         return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
-                                num_rois, pool_mode, stream);
+                                num_rois, pool_mode, zero_first ? 0 : 1, stream);
     }
     // the band-owner kernel (roi_align_bwd_band.cu) keeps maps of any size plane-resident (a CTA owns a slab of rows):
     // AUTO takes it where the phased kernel cannot hold 16 whole planes (1.7 ms against 1.49 ms on config 2 otherwise)
@@ -1041,18 +1051,53 @@ extern "C" int i2v_roi_align_backward(const float* grad_out, const float* featur
 }
 
 // ---- the reference-signature launchers (roi_align_kernel.h:13-27) ----
+// roi_align_kernel.h:13-17 does not pass the batch size, and the plane-resident kernels are launched per frame: the
+// largest frame index of the RoI list is found on the device and read back (one 4-byte copy and one stream
+// synchronisation per call).
+__global__ void max_frame_kernel(const float* __restrict__ rois, int num_rois, int* __restrict__ out) {
+    int m = -1;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < num_rois; n += gridDim.x * blockDim.x)
+        m = max(m, (int)fminf(fmaxf(__ldg(rois + (size_t)n * 5), -1.f), 1.0e9f));
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(out, m);
+}
+constexpr int kLegacyMaxFrames = 4096;   // beyond this the launcher keeps to the gather kernel (no per-frame lists)
+
 extern "C" int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
                                       const int height, const int width, const int channels, const int aligned_height,
                                       const int aligned_width, const float* bottom_rois, float* top_data,
                                       cudaStream_t stream) {
     if (num_rois < 0) return 0;
     size_t have = 0;
-    void* ws = legacy_scratch(carve_lattice_ws(nullptr, 0, num_rois, false).bytes, &have);
+    const size_t gather_bytes = carve_lattice_ws(nullptr, 0, num_rois, false).bytes;
+    char* ws = static_cast<char*>(legacy_scratch(gather_bytes + 256, &have, stream));
     if (!ws) return 0;
-    // roi_align_kernel.h:13-17 does not pass the batch size: every non-negative frame index is accepted
+    int frames = INT32_MAX;     // roi_align_kernel.h:13-17: every non-negative frame index is accepted
+    if (num_rois > 0 && aligned_height == 7 && aligned_width == 7 && channels % 16 == 0) {
+        int* d_max = reinterpret_cast<int*>(ws);
+        int h_max = -1;
+        if (cudaMemsetAsync(d_max, 0xff, sizeof(int), stream) != cudaSuccess) return 0;
+        max_frame_kernel<<<grid_for(num_rois, 256, 1), 256, 0, stream>>>(bottom_rois, num_rois, d_max);
+        if (cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess) {
+            set_error("ROIAlignForwardLaucher: reading the frame count back failed");
+            cudaGetLastError();
+            return 0;
+        }
+        if (h_max >= 0 && h_max < kLegacyMaxFrames) {
+            frames = h_max + 1;
+            const size_t need = i2v_roi_align_workspace_bytes(frames, num_rois);
+            ws = static_cast<char*>(legacy_scratch(need + 256, &have, stream));
+            if (!ws) return 0;
+            int rc = i2v_roi_align_forward(bottom_data, bottom_rois, top_data, frames, channels, height, width, num_rois,
+                                           aligned_height, aligned_width, spatial_scale, I2V_POOL_NONE, I2V_IMPL_AUTO,
+                                           ws + 256, have - 256, stream);
+            return rc == I2V_OK ? 1 : 0;
+        }
+    }
     int rc = i2v_roi_align_forward(bottom_data, bottom_rois, top_data, INT32_MAX, channels, height, width, num_rois,
-                                   aligned_height, aligned_width, spatial_scale, I2V_POOL_NONE, I2V_IMPL_GATHER, ws, have,
-                                   stream);
+                                   aligned_height, aligned_width, spatial_scale, I2V_POOL_NONE, I2V_IMPL_GATHER, ws + 256,
+                                   have - 256, stream);
     return rc == I2V_OK ? 1 : 0;
 }
 
@@ -1060,13 +1105,15 @@ extern "C" int ROIAlignBackwardLaucher(const float* top_diff, const float spatia
                                        const int num_rois, const int height, const int width, const int channels,
                                        const int aligned_height, const int aligned_width, const float* bottom_rois,
                                        float* bottom_diff, cudaStream_t stream) {
-    if (num_rois < 0) return 0;
+    if (num_rois < 0 || batch_size < 0) return 0;
     size_t have = 0;
-    void* ws = legacy_scratch(carve_lattice_ws(nullptr, 0, num_rois, false).bytes, &have);
+    // accumulates into the caller-zeroed bottom_diff like roi_align_kernel.cu:129-141: AUTO takes the phased kernel in
+    // its adding mode where the shape allows it (7x7 lattice, C % 16 == 0, 16 planes in shared memory), else the atomic
+    // gather kernel
+    void* ws = legacy_scratch(i2v_roi_align_workspace_bytes(batch_size, num_rois), &have, stream);
     if (!ws) return 0;
-    // accumulates into the caller-zeroed bottom_diff like roi_align_kernel.cu:129-141
     int rc = roi_align_backward_impl(top_diff, nullptr, bottom_rois, bottom_diff, batch_size, channels, height, width,
                                      num_rois, aligned_height, aligned_width, spatial_scale, I2V_POOL_NONE,
-                                     I2V_IMPL_GATHER, ws, have, false, stream);
+                                     I2V_IMPL_AUTO, ws, have, false, stream);
     return rc == I2V_OK ? 1 : 0;
 }

@@ -194,7 +194,7 @@ template <int POOL, int WT>
 __global__ void __launch_bounds__(kThreads, 1)
     lattice_bwd_phase_kernel(const float* __restrict__ grad_out, const PhaseTab* __restrict__ ptab,
                              const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ grad_in,
-                             int C, int H, int Wrt) {
+                             int C, int H, int Wrt, int accumulate) {
     constexpr int P = 7;
     constexpr int G = (POOL == I2V_POOL_NONE) ? P : P + 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int b = blockIdx.x / ctiles;
     const int list_lo = __ldg(starts + b), list_hi = __ldg(starts + b + 1);
     const int count = list_hi - list_lo;
+    // `accumulate`: add the planes to what grad_in holds (the reference launcher's contract, roi_align_kernel.cu:129-141:
+    // the caller zeroes bottom_diff and the kernel adds) instead of overwriting it; a frame without RoIs is left alone
+    if (accumulate && count == 0) return;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -366,7 +369,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         float* dst = grad_in + ((size_t)b * C + (size_t)ct * kK + (size_t)q * 4) * HW;
         const float4* src = reinterpret_cast<const float4*>(planes);
         for (int cell = warp * 8 + (lane >> 2); cell < HW; cell += kConsumers * 8) {
-            const float4 v = src[cell * 4 + q];
+            float4 v = src[cell * 4 + q];
+            if (accumulate) {
+                v.x += dst[cell];
+                v.y += dst[(size_t)HW + cell];
+                v.z += dst[(size_t)2 * HW + cell];
+                v.w += dst[(size_t)3 * HW + cell];
+            }
             dst[cell] = v.x;
             dst[(size_t)HW + cell] = v.y;
             dst[(size_t)2 * HW + cell] = v.z;
@@ -386,27 +395,29 @@ bool bwd_phase_ok(const float* grad_out, int batch, int C, int H, int W, int PH,
 
 template <int POOL, int WT>
 static int launch_phase(const float* grad_out, const PhaseTab* ptab, const int* order, const int* starts, float* grad_in,
-                        int batch, int C, int H, int W, cudaStream_t stream) {
+                        int batch, int C, int H, int W, int accumulate, cudaStream_t stream) {
     auto kern = lattice_bwd_phase_kernel<POOL, WT>;
     const size_t smem = bwd_phase_smem_bytes(H, W);
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)(batch * (C / kK))), kThreads, smem, stream>>>(grad_out, ptab, order, starts, grad_in, C, H, W);
+    kern<<<dim3((unsigned)(batch * (C / kK))), kThreads, smem, stream>>>(grad_out, ptab, order, starts, grad_in, C, H, W,
+                                                                            accumulate);
     return check_launch("lattice_bwd_phase_kernel");
 }
 
 // `tab` holds the LatticeRoi tables of this call; `tab_space` is the workspace's per-RoI table slot (kRoiTabSlotBytes each).
 int launch_bwd_phase(const float* grad_out, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts,
-                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream) {
+                     float* grad_in, int batch, int C, int H, int W, int num_rois, int pool_mode, int accumulate,
+                     cudaStream_t stream) {
     PhaseTab* ptab = static_cast<PhaseTab*>(tab_space);
     const int G = pool_mode == I2V_POOL_NONE ? 7 : 8;
     phase_prep_kernel<<<ceil_div(num_rois, 128), 128, 0, stream>>>(tab, ptab, num_rois, G, W,
                                                                     pool_mode == I2V_POOL_AVG ? 0.25f : 1.f);
     I2V_TRY(check_launch("phase_prep_kernel"));
     if (pool_mode == I2V_POOL_AVG) {
-        if (W == 63) return launch_phase<I2V_POOL_AVG, 63>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
-        return launch_phase<I2V_POOL_AVG, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
+        if (W == 63) return launch_phase<I2V_POOL_AVG, 63>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, accumulate, stream);
+        return launch_phase<I2V_POOL_AVG, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, accumulate, stream);
     }
-    return launch_phase<I2V_POOL_NONE, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, stream);
+    return launch_phase<I2V_POOL_NONE, 0>(grad_out, ptab, order, starts, grad_in, batch, C, H, W, accumulate, stream);
 }
 
 }  // namespace i2v

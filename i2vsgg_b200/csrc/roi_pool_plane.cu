@@ -138,13 +138,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     continue;
                 }
                 // half 0 takes rows hs, hs+2, ...; half 1 rows hs+1, hs+3, ...: same column, opposite bank half.
-                // A bin is at most 12 rows tall (H <= 77, checked on the host).
+                // The sweep is specialised on the bin height up to 12 rows; taller bins (a RoI reaching far past the map:
+                // rs and re are not clipped, roi_pooling_kernel.cu:60-66) take the generic loop below.
                 const int nr = he - hs;
                 const int myrows = (nr - half + 1) >> 1;
                 constexpr int kRow2 = 2 * kPitch * kK;          // two rows further down, in floats
                 // a one-row bin leaves half 1 without a row of its own: it re-reads half 0's
                 const float* rowp = lane_base + (size_t)(hs + (nr > 1 ? half : 0)) * kPitch * kK;
-                if (regular) {
+                if (regular && nr <= 12) {
                     const int x0 = __shfl_sync(0xffffffffu, lo, 7);
                     const float* p = rowp + (size_t)x0 * kK;
                     const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int myrows = (nr - half + 1) >> 1;
                 constexpr int kRow2 = 2 * kPitch * 16;
                 const unsigned* rowp = lane_base + (size_t)(hs + (nr > 1 ? half : 0)) * kPitch * 16;
-                if (regular) {
+                if (regular && nr <= 12) {
                     const int x0 = __shfl_sync(0xffffffffu, lo, 7);
                     const unsigned* p = rowp + (size_t)x0 * 16;
                     const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;

@@ -69,6 +69,59 @@ __global__ void __launch_bounds__(256) pair_build_kernel(const float* __restrict
     }
 }
 
+// The pair stage of a whole frame group in ONE launch (faster_rcnn_SGG_emb.py:597-606,649-656 for every frame of the group):
+// blockIdx.y = frame; the first `pair_blocks` blocks of a frame write 256 pairs each (indices into the group's row
+// space f * N + i, union box with the frame number in column 0); the next N blocks paint one 32x32 object mask each.
+// The relation head forms a pair's two mask channels from its subject's and object's masks (conv_lo is linear in its
+// input channels), so the [P,2,32,32] pair masks -- 33 MB per 64-detection frame, of which 64 rows were read -- are not
+// written at all.
+__global__ void __launch_bounds__(256) pair_build_frames_kernel(const float* __restrict__ boxes, int N, int pair_blocks,
+                                                                float im_h, float im_w, float margin,
+                                                                int64_t* __restrict__ ixs, int64_t* __restrict__ ixo,
+                                                                float* __restrict__ rel_boxes,
+                                                                float* __restrict__ obj_masks) {
+    const int f = blockIdx.y;
+    const int P = N * (N - 1);
+    const float* fb = boxes + (size_t)f * N * 4;
+    if ((int)blockIdx.x < pair_blocks) {
+        const int p = blockIdx.x * 256 + threadIdx.x;
+        if (p >= P) return;
+        const int i = p / (N - 1);
+        const int jj = p - i * (N - 1);
+        const int j = jj + (jj >= i ? 1 : 0);
+        const float4 s = *reinterpret_cast<const float4*>(fb + (size_t)i * 4);
+        const float4 o = *reinterpret_cast<const float4*>(fb + (size_t)j * 4);
+        const size_t g = (size_t)f * P + p;
+        if (ixs) ixs[g] = (int64_t)f * N + i;
+        if (ixo) ixo[g] = (int64_t)f * N + j;
+        if (rel_boxes) {
+            const double m = (double)margin;
+            float* r = rel_boxes + g * 5;
+            r[0] = (float)f;
+            r[1] = (float)fmax(0.0, fmin((double)s.x, (double)o.x) - m);
+            r[2] = (float)fmax(0.0, fmin((double)s.y, (double)o.y) - m);
+            r[3] = (float)fmin((double)im_w, fmax((double)s.z, (double)o.z) + m);
+            r[4] = (float)fmin((double)im_h, fmax((double)s.w, (double)o.w) + m);
+        }
+        return;
+    }
+    if (!obj_masks) return;
+    const int i = blockIdx.x - pair_blocks;
+    const double rh = 32.0 / (double)im_h, rw = 32.0 / (double)im_w;
+    int x1, x2, y1, y2;
+    mask_extent(fb + (size_t)i * 4, rh, rw, x1, x2, y1, y2);
+    float4* dst = reinterpret_cast<float4*>(obj_masks + ((size_t)f * N + i) * 1024);
+    const int v = threadIdx.x;                 // float4 index inside the 32x32 mask
+    const int y = v >> 3, xb = (v & 7) * 4;
+    const bool row = (y >= y1 && y < y2);
+    float4 mk;
+    mk.x = (row && xb + 0 >= x1 && xb + 0 < x2) ? 1.f : 0.f;
+    mk.y = (row && xb + 1 >= x1 && xb + 1 < x2) ? 1.f : 0.f;
+    mk.z = (row && xb + 2 >= x1 && xb + 2 < x2) ? 1.f : 0.f;
+    mk.w = (row && xb + 3 >= x1 && xb + 3 < x2) ? 1.f : 0.f;
+    dst[v] = mk;
+}
+
 // ------------------------------------------------------------------------------------------ triplet top-k
 constexpr int kTopThreads = 1024;
 constexpr int kTopMax = 1024;  // largest supported top_k
@@ -102,8 +155,14 @@ __global__ void __launch_bounds__(256) triplet_keys_kernel(const float* __restri
                                                            const float* __restrict__ conf,
                                                            const int64_t* __restrict__ ixs,
                                                            const int64_t* __restrict__ ixo, int total, int R,
-                                                           unsigned* __restrict__ keys, unsigned* __restrict__ ghist) {
+                                                           unsigned* __restrict__ keys, unsigned* __restrict__ ghist,
+                                                           int num_boxes) {
     __shared__ unsigned hist[kHistBins];
+    // blockIdx.y = frame of a group of frames with identical pair lists (ixs / ixo are frame-local)
+    rel_score += (size_t)blockIdx.y * total;
+    conf += (size_t)blockIdx.y * num_boxes;
+    keys += (size_t)blockIdx.y * total;
+    ghist += (size_t)blockIdx.y * (kHistBins + 64);
     for (int i = threadIdx.x; i < kHistBins; i += 256) hist[i] = 0;
     __syncthreads();
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
@@ -152,6 +211,10 @@ __global__ void __launch_bounds__(256) triplet_filter_kernel(const unsigned* __r
                                                              unsigned* __restrict__ counter,
                                                              unsigned long long* __restrict__ cand) {
     __shared__ unsigned s_bin;
+    keys += (size_t)blockIdx.y * total;
+    ghist += (size_t)blockIdx.y * (kHistBins + 64);
+    counter += (size_t)blockIdx.y * (kHistBins + 64);
+    cand += (size_t)blockIdx.y * kCandCap;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 32) {
         const unsigned b = threshold_bin(ghist, (unsigned)K, lane);
@@ -275,11 +338,21 @@ __global__ void __launch_bounds__(kTopThreads) triplet_select_kernel(
     const int64_t* __restrict__ classes, const float* __restrict__ boxes, const int64_t* __restrict__ ixs,
     const int64_t* __restrict__ ixo, int P, int R, int top_k, const unsigned* __restrict__ keys,
     const unsigned* __restrict__ counter, const unsigned long long* __restrict__ cand_list,
-    float* __restrict__ record_out, int* __restrict__ count_out) {
+    float* __restrict__ record_out, int* __restrict__ count_out, int num_boxes) {
     extern __shared__ __align__(16) unsigned long long cand[];
     __shared__ unsigned hist[kHistBins];
     const int tid = threadIdx.x;
     const int total = P * R;
+    {   // blockIdx.x = frame
+        const size_t f = blockIdx.x;
+        classes += f * num_boxes;
+        boxes += f * num_boxes * 4;
+        keys += f * total;
+        counter += f * (kHistBins + 64);
+        cand_list += f * kCandCap;
+        record_out += f * top_k * 13;
+        if (count_out) count_out += f;
+    }
     const int K = min(top_k, total);
     const unsigned M = K > 0 ? *counter : 0u;
     int n_sort = K;
@@ -353,54 +426,86 @@ extern "C" int i2v_pair_build(const float* boxes, int num_boxes, float im_h, flo
 }
 
 struct TopkWs {
-    unsigned* keys;
-    unsigned* hist;             // [kHistBins] followed by the candidate counter
-    unsigned* counter;
-    unsigned long long* cand;   // [kCandCap]
+    unsigned* keys;             // [frames][pairs * rel]
+    unsigned* hist;             // [frames][kHistBins + 64]: the histogram followed by the candidate counter
+    unsigned long long* cand;   // [frames][kCandCap]
     size_t bytes;
 };
-static TopkWs carve_topk_ws(void* ws, int num_pairs, int num_rel) {
+static TopkWs carve_topk_ws(void* ws, int frames, int num_pairs, int num_rel) {
     Carver cv(ws);
     TopkWs w{};
-    w.keys = cv.take<unsigned>((size_t)num_pairs * num_rel);
-    w.hist = cv.take<unsigned>(kHistBins + 64);
-    w.counter = w.hist + kHistBins;
-    w.cand = cv.take<unsigned long long>(kCandCap);
+    w.keys = cv.take<unsigned>((size_t)frames * num_pairs * num_rel);
+    w.hist = cv.take<unsigned>((size_t)frames * (kHistBins + 64));
+    w.cand = cv.take<unsigned long long>((size_t)frames * kCandCap);
     w.bytes = cv.used();
     return w;
 }
 
 extern "C" size_t i2v_triplet_topk_workspace_bytes(int num_pairs, int num_rel) {
     if (num_pairs < 0 || num_rel < 0) return 0;
-    return carve_topk_ws(nullptr, num_pairs, num_rel).bytes;
+    return carve_topk_ws(nullptr, 1, num_pairs, num_rel).bytes;
+}
+extern "C" size_t i2v_triplet_topk_frames_workspace_bytes(int frames, int num_pairs, int num_rel) {
+    if (frames < 0 || num_pairs < 0 || num_rel < 0) return 0;
+    return carve_topk_ws(nullptr, frames, num_pairs, num_rel).bytes;
+}
+
+extern "C" int i2v_triplet_topk_frames(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
+                                       const int64_t* ixs, const int64_t* ixo, int frames, int num_boxes, int num_pairs,
+                                       int num_rel, int top_k, float* record_out, int* count_out, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+    I2V_REQUIRE(frames >= 0 && num_boxes >= 0 && num_pairs >= 0 && num_rel >= 0 && top_k >= 1 && top_k <= kTopMax,
+                "triplet_topk: bad size (top_k <= %d)", kTopMax);
+    I2V_REQUIRE((int64_t)num_pairs * num_rel <= INT32_MAX && frames <= 65535, "triplet_topk: too many scores or frames");
+    if (frames == 0) return I2V_OK;
+    I2V_REQUIRE(record_out, "triplet_topk: null record_out");
+    const int total = num_pairs * num_rel;
+    const size_t need = i2v_triplet_topk_frames_workspace_bytes(frames, num_pairs, num_rel);
+    if (total > 0) I2V_REQUIRE(rel_score && conf && classes && boxes && ixs && ixo, "triplet_topk: null pointer");
+    if (!workspace || workspace_bytes < need) {
+        set_error("triplet_topk: workspace %zu < %zu bytes", workspace_bytes, need);
+        return I2V_ERR_WORKSPACE;
+    }
+    const TopkWs w = carve_topk_ws(workspace, frames, num_pairs, num_rel);
+    I2V_CUDA_TRY(cudaMemsetAsync(w.hist, 0, (size_t)frames * (kHistBins + 64) * sizeof(unsigned), stream));
+    if (total > 0) {
+        const int per_frame = std::max(1, 2 * kNumSMs / frames);
+        const int gx = (int)std::min<int64_t>(per_frame, ((int64_t)total + 255) / 256);
+        const dim3 grid((unsigned)gx, (unsigned)frames);
+        triplet_keys_kernel<<<grid, 256, 0, stream>>>(rel_score, conf, ixs, ixo, total, num_rel, w.keys, w.hist, num_boxes);
+        I2V_TRY(check_launch("triplet_keys_kernel"));
+        triplet_filter_kernel<<<grid, 256, 0, stream>>>(w.keys, total, std::min(top_k, total), w.hist, w.hist + kHistBins,
+                                                        w.cand);
+        I2V_TRY(check_launch("triplet_filter_kernel"));
+    }
+    const size_t smem = (size_t)kCandCap * sizeof(unsigned long long);
+    I2V_CUDA_TRY(cudaFuncSetAttribute(triplet_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    triplet_select_kernel<<<frames, kTopThreads, smem, stream>>>(classes, boxes, ixs, ixo, num_pairs, num_rel, top_k, w.keys,
+                                                                w.hist + kHistBins, w.cand, record_out, count_out, num_boxes);
+    return check_launch("triplet_select_kernel");
 }
 
 extern "C" int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
                                 const int64_t* ixs, const int64_t* ixo, int num_pairs, int num_rel, int top_k,
                                 float* record_out, int* count_out, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream) {
-    I2V_REQUIRE(num_pairs >= 0 && num_rel >= 0 && top_k >= 1 && top_k <= kTopMax, "triplet_topk: bad size (top_k <= %d)", kTopMax);
-    I2V_REQUIRE((int64_t)num_pairs * num_rel <= INT32_MAX, "triplet_topk: too many scores");
-    I2V_REQUIRE(record_out, "triplet_topk: null record_out");
-    const int total = num_pairs * num_rel;
-    const size_t need = i2v_triplet_topk_workspace_bytes(num_pairs, num_rel);
-    if (total > 0) I2V_REQUIRE(rel_score && conf && classes && boxes && ixs && ixo, "triplet_topk: null pointer");
-    if (!workspace || workspace_bytes < need) {
-        set_error("triplet_topk: workspace %zu < %zu bytes", workspace_bytes, need);
-        return I2V_ERR_WORKSPACE;
-    }
-    const TopkWs w = carve_topk_ws(workspace, num_pairs, num_rel);
-    I2V_CUDA_TRY(cudaMemsetAsync(w.hist, 0, (kHistBins + 64) * sizeof(unsigned), stream));
-    if (total > 0) {
-        const int grid = (int)std::min<int64_t>(2 * kNumSMs, ((int64_t)total + 255) / 256);
-        triplet_keys_kernel<<<grid, 256, 0, stream>>>(rel_score, conf, ixs, ixo, total, num_rel, w.keys, w.hist);
-        I2V_TRY(check_launch("triplet_keys_kernel"));
-        triplet_filter_kernel<<<grid, 256, 0, stream>>>(w.keys, total, std::min(top_k, total), w.hist, w.counter, w.cand);
-        I2V_TRY(check_launch("triplet_filter_kernel"));
-    }
-    const size_t smem = (size_t)kCandCap * sizeof(unsigned long long);
-    I2V_CUDA_TRY(cudaFuncSetAttribute(triplet_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    triplet_select_kernel<<<1, kTopThreads, smem, stream>>>(classes, boxes, ixs, ixo, num_pairs, num_rel, top_k, w.keys,
-                                                           w.counter, w.cand, record_out, count_out);
-    return check_launch("triplet_select_kernel");
+    // one frame; the strides of the frame dimension are never used
+    return i2v_triplet_topk_frames(rel_score, conf, classes, boxes, ixs, ixo, 1, 0, num_pairs, num_rel, top_k, record_out,
+                                   count_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int i2v_pair_build_frames(const float* boxes, int frames, int num_boxes, float im_h, float im_w, float margin,
+                                     int64_t* ixs, int64_t* ixo, float* rel_boxes, float* obj_masks, cudaStream_t stream) {
+    I2V_REQUIRE(frames >= 0 && num_boxes >= 0 && frames <= 65535, "pair_build_frames: bad size");
+    if (frames == 0 || num_boxes == 0) return I2V_OK;
+    I2V_REQUIRE(boxes && ((uintptr_t)boxes & 15) == 0, "pair_build_frames: boxes must be a 16-byte aligned device pointer");
+    I2V_REQUIRE((int64_t)frames * num_boxes * (num_boxes - 1) <= INT32_MAX, "pair_build_frames: too many pairs");
+    I2V_REQUIRE(!obj_masks || ((uintptr_t)obj_masks & 15) == 0, "pair_build_frames: masks must be 16-byte aligned");
+    const int P = num_boxes * (num_boxes - 1);
+    const int pair_blocks = num_boxes >= 2 ? (P + 255) / 256 : 0;
+    const dim3 grid((unsigned)(pair_blocks + (obj_masks ? num_boxes : 0)), (unsigned)frames);
+    if (grid.x == 0) return I2V_OK;
+    pair_build_frames_kernel<<<grid, 256, 0, stream>>>(boxes, num_boxes, pair_blocks, im_h, im_w, margin, ixs, ixo, rel_boxes,
+                                                       obj_masks);
+    return check_launch("pair_build_frames_kernel");
 }

@@ -10,14 +10,14 @@ import torch
 
 from . import _lib
 from ._lib import (ARGMAX_FLAT, ARGMAX_PLANE, DT_BF16, DT_F32, DT_TF32, IMPL_AUTO, IMPL_BAND, IMPL_GATHER, IMPL_PHASE, IMPL_PLANE,
-                   IMPL_ROWS,
+                   IMPL_ROWS, IMPL_SLAB,
                    POOL_AVG, POOL_MAX, POOL_NONE, check, load)
 
 _POOLS = {"none": POOL_NONE, "avg": POOL_AVG, "max": POOL_MAX, POOL_NONE: POOL_NONE, POOL_AVG: POOL_AVG,
           POOL_MAX: POOL_MAX}
-_IMPLS = {"auto": IMPL_AUTO, "gather": IMPL_GATHER, "plane": IMPL_PLANE, "rows": IMPL_ROWS, "phase": IMPL_PHASE, "band": IMPL_BAND,
+_IMPLS = {"auto": IMPL_AUTO, "gather": IMPL_GATHER, "plane": IMPL_PLANE, "rows": IMPL_ROWS, "phase": IMPL_PHASE, "band": IMPL_BAND, "slab": IMPL_SLAB,
           IMPL_AUTO: IMPL_AUTO, IMPL_GATHER: IMPL_GATHER, IMPL_PLANE: IMPL_PLANE, IMPL_ROWS: IMPL_ROWS, IMPL_PHASE: IMPL_PHASE,
-          IMPL_BAND: IMPL_BAND}
+          IMPL_BAND: IMPL_BAND, IMPL_SLAB: IMPL_SLAB}
 
 
 def _p(t):
@@ -261,6 +261,46 @@ def triplet_topk(rel_score, conf, classes, boxes, ixs, ixo, top_k: int = 100):
         ws = _workspace(lib.i2v_triplet_topk_workspace_bytes(P, R), dev)
         check(lib.i2v_triplet_topk(_p(rel_score), _p(conf), _p(classes), _p(boxes), _p(ixs), _p(ixo), P, R,
                                    int(top_k), _p(rec), _p(cnt), _p(ws), ws.numel(), _stream()), "i2v_triplet_topk")
+    return rec, cnt
+
+
+def pair_build_frames(boxes, im_h: float, im_w: float, margin: float = 10.0, want_masks: bool = True):
+    """boxes [F,N,4] -> (ixs [F*P], ixo [F*P] int64 = group rows f*N+i, rel_boxes [F*P,5] with the frame number in column
+    0, obj_masks [F*N,32,32] or None): the pair stage of a whole frame group in one launch."""
+    boxes = _f32(boxes, "boxes")
+    if boxes.dim() != 3 or boxes.size(2) != 4:
+        raise _lib.I2VError(f"pair_build_frames: boxes must be [F,N,4], got {tuple(boxes.shape)}")
+    F, N = boxes.shape[:2]
+    P = N * (N - 1) if N > 1 else 0
+    dev = boxes.device
+    ixs = torch.empty((F * P,), dtype=torch.int64, device=dev)
+    ixo = torch.empty((F * P,), dtype=torch.int64, device=dev)
+    rel = torch.empty((F * P, 5), dtype=torch.float32, device=dev)
+    masks = torch.empty((F * N, 32, 32), dtype=torch.float32, device=dev) if want_masks else None
+    with torch.cuda.device(dev):
+        check(load().i2v_pair_build_frames(_p(boxes), F, N, float(im_h), float(im_w), float(margin), _p(ixs), _p(ixo),
+                                           _p(rel), _p(masks), _stream()), "i2v_pair_build_frames")
+    return ixs, ixo, rel, masks
+
+
+def triplet_topk_frames(rel_score, conf, classes, boxes, ixs, ixo, top_k: int = 100):
+    """lib/utils.py:609-626 for F frames of N detections each in three launches: rel_score [F*P,R], conf / classes [F,N],
+    boxes [F,N,4], ixs / ixo [P] frame-local -> (records [F,top_k,13], counts [F] int32)."""
+    rel_score, conf, boxes = _f32(rel_score, "rel_score"), _f32(conf, "conf"), _f32(boxes, "boxes")
+    classes, ixs, ixo = classes.long().contiguous(), ixs.long().contiguous(), ixo.long().contiguous()
+    F, N = conf.shape
+    P, R = ixs.numel(), rel_score.size(1)
+    if rel_score.size(0) != F * P or classes.shape != (F, N) or boxes.shape != (F, N, 4):
+        raise _lib.I2VError("triplet_topk_frames: shapes do not describe F frames of N detections")
+    dev = rel_score.device
+    rec = torch.empty((F, top_k, 13), dtype=torch.float32, device=dev)
+    cnt = torch.empty((F,), dtype=torch.int32, device=dev)
+    lib = load()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.i2v_triplet_topk_frames_workspace_bytes(F, P, R), dev)
+        check(lib.i2v_triplet_topk_frames(_p(rel_score), _p(conf), _p(classes), _p(boxes), _p(ixs), _p(ixo), F, N, P, R,
+                                          int(top_k), _p(rec), _p(cnt), _p(ws), ws.numel(), _stream()),
+              "i2v_triplet_topk_frames")
     return rec, cnt
 
 

@@ -82,6 +82,9 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
                               channel); conflict-free, CTA barrier between feature-row phases (forward: like PLANE)    */
 #define I2V_IMPL_BAND 5    /* backward only: lanes = 32 channels, a CTA owns a slab of feature rows of (frame, 32
                               channels), each warp a band of those rows: no ordering between warps (forward: like PLANE) */
+#define I2V_IMPL_SLAB 6    /* forward only: the 16 planes of a CTA arrive as one TMA bulk copy and are used in place as
+                              [channel][row][col] (what AUTO picks for 38x63 / 63x38 maps); I2V_ERR_UNSUPPORTED elsewhere
+                              and in the backward                                                                          */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.
@@ -164,6 +167,13 @@ int i2v_proposal_stages(const float* cls_prob, const float* bbox_pred, const flo
 int i2v_pair_build(const float* boxes, int num_boxes, float im_h, float im_w, float margin, int64_t* ixs,
                    int64_t* ixo, float* rel_boxes, float* masks, cudaStream_t stream);
 
+/* The pair stage of a frame GROUP in one launch (the loops of faster_rcnn_SGG_emb.py:597-606,649-656 for every frame):
+ * boxes [F,N,4] (16-byte aligned) -> ixs, ixo [F*P] int64 holding GROUP rows f*N+i, rel_boxes [F*P,5] with the frame
+ * number f in column 0, obj_masks [F*N,32,32] fp32 = the mask of resnet_SGG_emb.py:246-256 once per OBJECT (a pair's
+ * two mask channels are its subject's and its object's mask).  Any output may be NULL. */
+int i2v_pair_build_frames(const float* boxes, int frames, int num_boxes, float im_h, float im_w, float margin,
+                          int64_t* ixs, int64_t* ixo, float* rel_boxes, float* obj_masks, cudaStream_t stream);
+
 /* ---- 8. Triplet top-k (lib/utils.py:609-626) ------------------------------------------------ */
 size_t i2v_triplet_topk_workspace_bytes(int num_pairs, int num_rel);
 /* rel_score [P,R]; conf [N]; classes [N] int64; boxes [N,4]; ixs/ixo [P] int64.
@@ -173,6 +183,15 @@ int i2v_triplet_topk(const float* rel_score, const float* conf, const int64_t* c
                      const int64_t* ixs, const int64_t* ixo, int num_pairs, int num_rel, int top_k,
                      float* record_out, int* count_out, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream);
+
+/* The same for F frames with the same number of detections in three launches: rel_score [F*P,R], conf / classes
+ * [F,N], boxes [F,N,4]; ixs / ixo [P] are the FRAME-LOCAL pair lists (identical for every frame); record_out
+ * [F,top_k,13], count_out [F]. */
+size_t i2v_triplet_topk_frames_workspace_bytes(int frames, int num_pairs, int num_rel);
+int i2v_triplet_topk_frames(const float* rel_score, const float* conf, const int64_t* classes, const float* boxes,
+                            const int64_t* ixs, const int64_t* ixo, int frames, int num_boxes, int num_pairs,
+                            int num_rel, int top_k, float* record_out, int* count_out, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- 9. Embedding projection of the SGG stage (resnet_SGG_emb.py:128-221) ---- */
 #define I2V_DT_F32 0   /* fp32 storage                                                        */

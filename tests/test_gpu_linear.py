@@ -198,3 +198,23 @@ def test_roi_pool_rows_bf16_planes_equal_fp32_planes(ops, shape):
     assert torch.equal(got, ref)
     want, _ = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16, ARGMAX_PLANE)
     assert torch.equal(got, want.reshape(N, -1).bfloat16())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roi_pool_rows_with_rois_far_larger_than_the_map(ops, dtype):
+    """RoIs reaching far past the map are legal (the start / end rows are clamped per bin, roi_pooling_kernel.cu:60-66), and
+    their bins can be taller than the 12 rows the row sweep is specialised for (rs = -38, re = 76 on a 38-row map: bin 3
+    covers rows 11..28): those take the generic loop and must equal the exact RoIPool op."""
+    from i2vsgg_b200._lib import ARGMAX_PLANE
+    B, C, H, W = 1, 64, 38, 63
+    g = torch.Generator(device="cuda").manual_seed(77)
+    feat = torch.randn((B, C, H, W), device="cuda", generator=g) * 2
+    r = np.array([[0, -600, -608, 1600, 1216],       # rs = -38, re = 76 in rows
+                  [0, -3000, -2000, 4000, 2600],
+                  [0, 100, -900, 400, 1500],          # tall and narrow
+                  [0, -2000, 100, 3000, 300],         # wide and low
+                  [0, 0, 0, 999, 599]], np.float32)
+    rois = torch.from_numpy(r).cuda()
+    want, _ = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16, ARGMAX_PLANE)
+    got = ops.roi_pool_rows(feat, rois, 7, 7, 1 / 16, dtype=dtype)
+    assert torch.equal(got, want.reshape(len(r), -1).to(dtype))

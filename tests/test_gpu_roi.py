@@ -294,6 +294,54 @@ def test_legacy_launchers(ops, orc):
     close(pg, orc.roi_pool_backward(g7, rois, wa, feat.shape, 7, 7, SCALE))
 
 
+def test_legacy_launchers_take_the_fast_kernels(ops):
+    """roi_align_kernel.h:13-27 at config-2 width (1024 channels, 7x7 lattice): the launchers must run the plane-resident
+    kernels -- same numbers as the i2v_* entry points (the backward ADDS into the caller's buffer like the reference's
+    atomicAdd scatter) and within 1.3x of their time.  The forward launcher pays one 4-byte read-back per call for the
+    frame count its signature lacks."""
+    import ctypes
+    from i2vsgg_b200 import _lib
+    lib = _lib.load()
+    B, C, H, W, N = 8, 1024, 38, 63, 2400
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    feat = torch.randn((B, C, H, W), device="cuda", generator=gen)
+    rois = cuda(synth.rois(77, N, batch=B, sort_by_batch=False))
+    grad = torch.randn((N, C, 7, 7), device="cuda", generator=gen)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = torch.empty((N, C, 7, 7), device="cuda")
+    fwd_legacy = lambda: lib.ROIAlignForwardLaucher(P(feat), SCALE, N, H, W, C, 7, 7, P(rois), P(out), s)
+    assert fwd_legacy() == 1
+    want = ops.roi_align_forward(feat, rois, 7, 7, SCALE, "none", "auto")
+    assert torch.equal(out, want)
+    t_legacy, t_entry = timed(fwd_legacy), timed(lambda: ops.roi_align_forward(feat, rois, 7, 7, SCALE, "none", "auto"))
+    assert t_legacy <= 1.3 * t_entry, (t_legacy, t_entry)
+
+    gin = torch.zeros((B, C, H, W), device="cuda")
+    bwd_legacy = lambda: lib.ROIAlignBackwardLaucher(P(grad), SCALE, B, N, H, W, C, 7, 7, P(rois), P(gin), s)
+    assert bwd_legacy() == 1
+    gwant = ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "none", "auto")
+    assert torch.equal(gin, gwant)
+    assert bwd_legacy() == 1                                   # a second call adds the same planes again
+    assert float((gin - 2 * gwant).abs().max()) <= 1e-6 * float(gwant.abs().max())
+    t_legacy = timed(bwd_legacy)
+    t_entry = timed(lambda: ops.roi_align_backward(grad, None, rois, (B, C, H, W), 7, 7, SCALE, "none", "auto"))
+    assert t_legacy <= 1.3 * t_entry, (t_legacy, t_entry)
+
+
 def _portrait_rois(seed, n, batch):
     r = synth.rois(seed, n, batch=batch)
     return np.ascontiguousarray(r[:, [0, 2, 1, 4, 3]])          # swap x and y: boxes of a 1000 x 600 (h x w) frame

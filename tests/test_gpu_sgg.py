@@ -117,3 +117,33 @@ def test_triplet_topk_config3_size_is_reproducible(ops, orc):
     rec = first.cpu().numpy()
     assert np.array_equal(rec[:, 0], wconf) and np.array_equal(rec[:, 1:4], wlab)
     assert np.array_equal(rec[:, 12].astype(np.int64), wpair)
+
+
+def test_frame_group_launches_equal_the_per_frame_ones():
+    """`pair_build_frames` / `triplet_topk_frames` (one launch chain per frame GROUP) against the per-frame entry points, bit
+    for bit: pair lists in group rows, union boxes with the frame number in column 0, one mask per object (= the subject
+    channel of that object's first pair), and the top-100 records of every frame -- ties included."""
+    import torch
+    from i2vsgg_b200 import ops, synth
+    F, N, R = 5, 11, 132
+    boxes, classes, conf = synth.clip_detections(3, F, N)
+    b = torch.from_numpy(boxes).cuda()
+    P = N * (N - 1)
+    ixs, ixo, rel, om = ops.pair_build_frames(b, synth.IM_H, synth.IM_W)
+    assert ixs.shape == (F * P,) and rel.shape == (F * P, 5) and om.shape == (F * N, 32, 32)
+    first = torch.arange(N, device="cuda") * (N - 1)
+    for f in range(F):
+        i1, o1, r1, m1 = ops.pair_build(b[f], synth.IM_H, synth.IM_W)
+        assert torch.equal(ixs[f * P:(f + 1) * P], i1 + f * N) and torch.equal(ixo[f * P:(f + 1) * P], o1 + f * N)
+        r1[:, 0] = f
+        assert torch.equal(rel[f * P:(f + 1) * P], r1)
+        assert torch.equal(om[f * N:(f + 1) * N], m1[first, 0])
+    g = torch.Generator(device="cuda").manual_seed(9)
+    scores = torch.rand((F * P, R), device="cuda", generator=g)
+    scores[:, ::7] = 0.5                               # plenty of exact ties
+    c = torch.from_numpy(np.tile(classes, (F, 1))).cuda()
+    s = torch.from_numpy(np.tile(conf, (F, 1))).cuda() * torch.linspace(0.5, 1.0, F, device="cuda")[:, None]
+    rec, cnt = ops.triplet_topk_frames(scores, s, c, b, ixs[:P], ixo[:P], 100)
+    for f in range(F):
+        want, wc = ops.triplet_topk(scores[f * P:(f + 1) * P], s[f], c[f], b[f], ixs[:P], ixo[:P], 100)
+        assert torch.equal(rec[f], want) and int(cnt[f]) == int(wc[0])
