@@ -37,6 +37,13 @@ WORKLOAD = ("configs[1]: 32 VidVRD-shaped frames (600x1000 -> conv4 1024x38x63),
             "proposals per frame, proposal decode + NMS + RoIAlignAvg 7x7 fwd + bwd")
 
 
+def config_dict(world: int):
+    """What the workload is -- identical in the GPU arm and the reference arm (the driver compares the two)."""
+    return {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "rois_per_gpu": FRAMES * POST_NMS,
+            "l2": "inputs larger than L2 (314 MB features, 1.9 GB pooled tensor and gradient per step)",
+            "parallelism": f"frames sharded over {world} rank(s), no data-path collective"}
+
+
 def algorithmic_bytes(frames: int, rois: int):
     """every feature byte once + rois + the pooled tensor (fwd); pooled gradient read +
     feature gradient written (bwd)."""
@@ -143,7 +150,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": sample_frames},
+            "config": config_dict(int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -235,6 +242,30 @@ def run_ours(args):
         barrier()
     e2e_ms = reduce_max(start2.elapsed_time(end2))
 
+    # ---- parity of the very buffers that were timed (outside the timed regions): the proposals of frames 0 and 17
+    # against the oracle's proposal layer, three of their pooled rows against the oracle's RoIAlignAvg
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle
+        pipe.device_step(cls_d, reg_d, info_d, feat_d, grad_d)
+        torch.cuda.synchronize()
+        fr = [0, 17]
+        want = oracle.proposal_layer(cls_h[fr].numpy(), reg_h[fr].numpy(), info_h[fr].numpy(), PRE_NMS, POST_NMS, NMS_THRESH)
+        got = pipe.rois[fr].cpu().numpy().copy()
+        got[:, :, 0] = np.arange(len(fr))[:, None]
+        rois_equal = bool(np.array_equal(got, want))
+        rows = [5, 150, 299]
+        sub = feat_h[17:18].numpy()
+        r3 = want[1, rows].copy()
+        r3[:, 0] = 0
+        pw = oracle.roi_align_pooled_forward(sub, r3, POOLED, POOLED, SCALE, "avg", nthreads=oracle.default_threads())
+        pg = pipe.pooled[[17 * POST_NMS + k for k in rows]].cpu().numpy()
+        err = float(np.abs(pg - pw).max() / max(np.abs(pw).max(), 1e-30))
+        parity = {"rois_equal_oracle": rois_equal, "pooled_max_rel_err": err, "frames_checked": fr, "rows_checked": rows}
+        assert rois_equal and err <= 1e-5, f"the timed buffers differ from the oracle: {parity}"
+
+    extra = {} if args.no_configs else other_configs(dev, rank, world, args.clip_frames)
+
     if rank == 0:
         alg = algorithmic_bytes(FRAMES, FRAMES * POST_NMS)
         top = max(("roi_align_fwd", "roi_align_bwd"), key=lambda k: stage_ms[k])
@@ -244,13 +275,11 @@ def run_ours(args):
             "metric": METRIC, "value": FRAMES * world * args.steps / (ms_total * 1e-3), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "rois_per_gpu": FRAMES * POST_NMS,
-                       "l2": "inputs larger than L2 (314 MB features, 1.9 GB pooled tensor and gradient per step)",
-                       "parallelism": f"frames sharded over {world} rank(s), no data-path collective",
-                       "pipelining": ("none" if args.no_pipeline else
-                                      "the proposal layer of step i+1 runs on a second stream under the RoIAlign backward of "
-                                      "step i; every step runs all three stages"),
-                       "ms_per_step_stage_by_stage": seq_ms},
+            "config": config_dict(world),
+            "pipelining": ("none" if args.no_pipeline else
+                           "the proposal layer of step i+1 runs on a second stream under the RoIAlign backward of step i; "
+                           "every step runs all three stages"),
+            "ms_per_step_stage_by_stage": seq_ms,
             "clocks": sampler.summary(),
             "e2e": {"value": FRAMES * world * e_steps / (e2e_ms * 1e-3) if e_steps else None, "unit": "frames/s", "steps": e_steps,
                     "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
@@ -258,11 +287,14 @@ def run_ours(args):
             "gpu_launches": launches,
             "stages_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic().get(top), "peak_source": which,
+                         "frac": achieved / peak, "traffic": measured_traffic().get(top),
+                         "traffic_source": measured_traffic().get("source"), "peak_source": which,
                          "algorithmic_bytes": alg[top],
                          "other": {k: {"achieved": alg[k] / (stage_ms[k] * 1e-3) / 1e9,
                                        "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / peak} for k in alg}},
         }
+        line["parity"] = parity
+        line.update(extra)
         if not args.no_projection:
             line["projection"] = projection_side_measurement(dev)
         if not args.no_cpu and world >= 1:
@@ -280,6 +312,131 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_configs(dev, rank: int, world: int, clip_frames_per_rank: int):
+    """BASELINE.json configs[2], [3] and [4], measured after the headline step (none of this is part of `value`).
+
+    sgg_frame  configs[2]: 64 detections -> 4032 ordered pairs: pair build + vrd.forward (union RoIPool, fc6/fc7/fc8 on
+               tcgen05, fusion, cosine scores) + top-100, ms per frame through ClipRunner (4 frames per launch group)
+    train_bwd  configs[3]: RoIAlignAvg backward, 8 images x 256 RoIs, gradient [2048,1024,7,7]
+    clip       configs[4]: a (128 x ranks)-frame clip, frames sharded over the ranks: proposal decode + NMS -> RoIAlignAvg
+               forward -> pair stage -> relation head -> top-100 -> ONE NCCL all-gather of the records -> temporal
+               association on rank 0.  Every rank takes part (the all-gather is a collective)."""
+    import torch
+    import torch.distributed as dist
+    from i2vsgg_b200 import ops, sgg, shard, synth
+    from i2vsgg_b200.clip import ClipRunner
+    from i2vsgg_b200.model.faster_rcnn.resnet_SGG_emb import vrd
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    tf_peak, hbm_peak = float(peaks.get("bf16_tflops", 1590.0)), float(peaks.get("hbm_gbs", 6650.0))
+
+    def timed(fn, warm=2, reps=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    vargs = synth.VrdArgs()
+    head = vrd(vargs, None, synth.prd_vectors(7))
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in synth.vrd_params(1234, vargs).items()})
+    head = head.to(dev).eval().prepare()
+    det = 64
+    group = 4
+    runner = ClipRunner(head, synth.IM_H, synth.IM_W, group)
+    fmap1 = torch.from_numpy(synth.feature_map(100 + rank, 1)).to(dev)
+
+    # ---- configs[2]
+    if rank == 0:
+        boxes, classes, conf = synth.clip_detections(5, group, det)
+        b = torch.from_numpy(boxes).to(dev)
+        c = torch.from_numpy(np.tile(classes, (group, 1))).to(dev)
+        s = torch.from_numpy(np.tile(conf, (group, 1))).to(dev)
+        fm = fmap1.expand(group, -1, -1, -1).contiguous()
+        ms = timed(lambda: runner._group(fm, b, c, s)) / group
+        P, N, U = det * (det - 1), det, det * (det - 1) // 2
+        flop = 2 * (U + N) * 50176 * 4096 + 2 * (U + N) * 4096 * 4096 + 2 * U * 4096 * 256 + 2 * N * 4096 * 300 \
+            + 2 * P * (600 + 768) * 256 + 2 * P * 256 * 300 + 2 * P * 300 * 132 \
+            + 2 * P * (256 * 50 * 96 + 64 * 2400 * 128 + 8192 * 64 + 64 * 256)
+        out["sgg_frame"] = {"workload": "configs[2]: 64 detections -> 4032 ordered pairs, pair build + vrd.forward + top-100, "
+                                        "4 frames per launch group", "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
+                            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tf_peak,
+                                         "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / tf_peak,
+                                         "flop_per_frame": flop,
+                                         "note": "whole frame (pooling, small layers, selection included) against the bf16 peak; "
+                                                 "flops counted with the unordered-pair shortcut"}}
+        del fm
+        # ---- configs[3]
+        B4, per = 8, 256
+        rois = torch.from_numpy(synth.rois(401, B4 * per, batch=B4, sort_by_batch=True)).to(dev)
+        grad = torch.randn((B4 * per, CHANNELS, POOLED, POOLED), device=dev)
+        ms4 = timed(lambda: ops.roi_align_backward(grad, None, rois, (B4, CHANNELS, FEAT_H, FEAT_W), POOLED, POOLED, SCALE,
+                                                   "avg"), warm=3, reps=20)
+        nbytes = grad.numel() * 4 + B4 * CHANNELS * FEAT_H * FEAT_W * 4 + rois.numel() * 4
+        out["train_bwd"] = {"workload": "configs[3]: RoIAlignAvg backward, 8 images x 256 RoIs, 1024 x 38 x 63", "ms": ms4,
+                            "roofline": {"bound": "hbm", "achieved": nbytes / (ms4 * 1e-3) / 1e9, "peak": hbm_peak,
+                                         "unit": "GB/s", "frac": nbytes / (ms4 * 1e-3) / 1e9 / hbm_peak,
+                                         "algorithmic_bytes": nbytes}}
+        del grad
+
+    # ---- configs[4]
+    frames = clip_frames_per_rank * world
+    lo, hi = shard.frame_range(frames, rank, world)
+    boxes, classes, conf = synth.clip_detections(5, frames, det)
+    b = torch.from_numpy(boxes[lo:hi]).to(dev)
+    c = torch.from_numpy(np.tile(classes, (hi - lo, 1))).to(dev)
+    s = torch.from_numpy(np.tile(conf, (hi - lo, 1))).to(dev)
+    nd = 8                                            # distinct RPN frames per rank, cycled over its chunk of the clip
+    cls_h, reg_h = synth.rpn_outputs(2000 + rank, batch=nd)
+    reps = (hi - lo + nd - 1) // nd
+    cls_d = torch.from_numpy(cls_h).to(dev).repeat(reps, 1, 1, 1)[: hi - lo]
+    reg_d = torch.from_numpy(reg_h).to(dev).repeat(reps, 1, 1, 1)[: hi - lo]
+    info_d = torch.from_numpy(synth.im_info(hi - lo)).to(dev)
+
+    class View:                                       # one seeded map per rank, handed out group by group
+        def __getitem__(self, sl):
+            n = len(range(*sl.indices(hi - lo)))
+            return fmap1.expand(n, -1, -1, -1).contiguous()
+
+    runner.run_full(cls_d[:group], reg_d[:group], info_d[:group], View(), b[:group], c[:group], s[:group], group * world,
+                    rank, world, pre_nms=PRE_NMS, post_nms=POST_NMS, nms_thresh=NMS_THRESH)        # warm-up, same collective
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tm = {}
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rec, cnt, kept = runner.run_full(cls_d, reg_d, info_d, View(), b, c, s, frames, rank, world, pre_nms=PRE_NMS,
+                                     post_nms=POST_NMS, nms_thresh=NMS_THRESH, timings=tm)
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(e), tm["gather_ms"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        t0 = time.perf_counter()
+        rels = sgg.association(rec, cnt)
+        assoc_ms = 1e3 * (time.perf_counter() - t0)
+        ms = float(t[0].item())
+        out["clip"] = {"workload": f"configs[4]: {frames}-frame synthetic VidVRD clip over {world} rank(s): proposal decode + NMS "
+                                   f"({PRE_NMS} -> {POST_NMS}), RoIAlignAvg 7x7 forward, {det} detections -> {det * (det - 1)} pairs, "
+                                   f"relation head, top-100 triplets, one all-gather of the records, temporal association on rank 0",
+                       "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+                       "gather": {"collective": "all_gather_into_tensor" if world > 1 else "none (one rank)",
+                                  "backend": "nccl" if world > 1 else None, "us": 1e3 * float(t[1].item()),
+                                  "gather_bytes": int(rec.numel() * 4 + cnt.numel() * 4)},
+                       "records_ok": bool(rec.shape == (frames, 100, 13) and int(cnt.min()) == 100),
+                       "proposals_kept_min": int(kept.min()) if kept.numel() else None,
+                       "association": {"ms": assoc_ms, "relations": len(rels)}}
+    return out
 
 
 def projection_side_measurement(dev):
@@ -321,6 +478,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per copy/compute chunk of the host-buffer leg")
     ap.add_argument("--no-projection", action="store_true", help="skip the relation-head side measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / [3] / [4] blocks")
+    ap.add_argument("--clip-frames", type=int, default=128, help="frames per rank of the configs[4] clip")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="run the three stages of a step strictly one after the other (no second stream)")
     args = ap.parse_args()

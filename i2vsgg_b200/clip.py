@@ -69,6 +69,44 @@ class ClipRunner:
                               obj_masks=obj_masks)
         return ops.triplet_topk_frames(scores, conf, classes, boxes, ixs[:P], ixo[:P], self.top_k)
 
+    def run_full(self, rpn_cls, rpn_reg, im_info, fmaps, boxes, classes, conf, num_frames: int, rank: int = 0,
+                 world: int = 1, group=None, pre_nms: int = 12000, post_nms: int = 300, nms_thresh: float = 0.7,
+                 spatial_scale: float = 1.0 / 16, timings: dict = None):
+        """BASELINE.json configs[4] end to end for this rank's frames: per frame group the RPN outputs (`rpn_cls`
+        [f,2A,H,W], `rpn_reg` [f,4A,H,W], `im_info` [f,3]) go through proposal decode + NMS (`ops.proposal_forward`), the
+        proposals through RoIAlignAvg 7x7 over `fmaps` (`ops.roi_align_forward`; the pooled rows are what the detector
+        head, out of scope here, would classify), and the frame's detections (`boxes`, `classes`, `conf`) through the pair
+        stage, the relation head and the top-100 selection (`_group`); then ONE all-gather puts the records of the whole
+        clip on every rank.  Returns (records [num_frames,top_k,13], counts [num_frames], proposals kept per frame).
+        `timings`, if given, receives the CUDA-event duration of the all-gather alone ("gather_ms")."""
+        from . import synth
+        lo, hi = shard.frame_range(num_frames, rank, world)
+        assert boxes.shape[0] == hi - lo, "pass exactly the frames of shard.frame_range(num_frames, rank, world)"
+        dev = boxes.device
+        anchors = torch.from_numpy(synth.BASE_ANCHORS).to(dev)
+        recs, cnts, kept = [], [], []
+        for f0 in range(0, hi - lo, self.group):
+            f1 = min(hi - lo, f0 + self.group)
+            fm = fmaps[f0:f1]
+            rois, nkeep = ops.proposal_forward(rpn_cls[f0:f1], rpn_reg[f0:f1], im_info[f0:f1], anchors, 16, pre_nms,
+                                               post_nms, nms_thresh, return_counts=True)
+            ops.roi_align_forward(fm, rois.reshape(-1, 5), 7, 7, spatial_scale, "avg")
+            step = self._group_replayed if self.graphs else self._group
+            r, c = step(fm, boxes[f0:f1], classes[f0:f1], conf[f0:f1])
+            recs.append(r)
+            cnts.append(c)
+            kept.append(nkeep)
+        rec = torch.cat(recs) if recs else torch.empty((0, self.top_k, shard.RECORD_WIDTH), device=dev)
+        cnt = torch.cat(cnts) if cnts else torch.empty((0,), dtype=torch.int32, device=dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = shard.all_gather_triplets(rec, cnt, num_frames, group)
+        b.record()
+        if timings is not None:
+            torch.cuda.synchronize()
+            timings["gather_ms"] = a.elapsed_time(b)
+        return out[0], out[1], (torch.cat(kept) if kept else torch.empty((0,), dtype=torch.int32, device=dev))
+
     def run(self, fmaps, boxes, classes, conf, num_frames: int, rank: int = 0, world: int = 1, group=None):
         """This rank's frames (`fmaps` [f,C,H,W], `boxes` [f,N,4], `classes` [f,N], `conf` [f,N], in clip order)
         -> (records [num_frames, top_k, 13], counts [num_frames]) of the WHOLE clip on every rank."""
