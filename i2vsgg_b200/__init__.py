@@ -22,6 +22,8 @@ _MODEL_MODULES = [
     "model.roi_align.modules", "model.roi_align.modules.roi_align",
     "model.roi_pooling", "model.roi_pooling.functions", "model.roi_pooling.functions.roi_pool",
     "model.roi_pooling.modules", "model.roi_pooling.modules.roi_pool",
+    "model.roi_crop", "model.roi_crop.functions", "model.roi_crop.functions.roi_crop",
+    "model.roi_crop.modules", "model.roi_crop.modules.roi_crop",
     "model.nms", "model.nms.nms_wrapper", "model.nms.nms_gpu",
     "model.rpn", "model.rpn.generate_anchors", "model.rpn.proposal_layer", "model.rpn.proposal_target_layer_cascade",
     "model.rpn.anchor_target_layer", "model.rpn.rpn",

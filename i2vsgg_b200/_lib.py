@@ -43,6 +43,10 @@ SIGNATURES = {
     "i2v_proposal_forward_scores": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "i2v_rpn_cls_prob": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "i2v_proposal_stages": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_roi_crop_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "i2v_roi_crop_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "BilinearSamplerBHWD_updateOutput_cuda_kernel": (_i, [_i] * 8 + [_vp] + [_i] * 4 + [_vp] + [_i] * 4 + [_vp] + [_i] * 4 + [_vp]),
+    "BilinearSamplerBHWD_updateGradInput_cuda_kernel": (_i, [_i] * 8 + ([_vp] + [_i] * 4) * 5 + [_vp]),
     "i2v_pair_build": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "i2v_pair_build_frames": (_i, [_vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "i2v_triplet_topk_workspace_bytes": (_sz, [_i, _i]),

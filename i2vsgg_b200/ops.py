@@ -232,6 +232,36 @@ def proposal_stages(cls_prob, bbox_pred, im_info, base_anchors, feat_stride: int
 
 
 # --------------------------------------------------------------------------------------- SGG pair stage
+def roi_crop_forward(features, grids):
+    """RoICropFunction.forward (functions/roi_crop.py:8-16): features [B,C,H,W], grids [N,oh,ow,2] = (y, x) in [-1,1]
+    -> [N,C,oh,ow]; RoI n samples frame n // (N // B)."""
+    features, grids = _f32(features, "features"), _f32(grids, "grids")
+    if features.dim() != 4 or grids.dim() != 4 or grids.size(3) != 2:
+        raise _lib.I2VError("roi_crop_forward: features [B,C,H,W] and grids [N,oh,ow,2] expected")
+    B, C, H, W = features.shape
+    N, oh, ow, _ = grids.shape
+    out = torch.empty((N, C, oh, ow), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(load().i2v_roi_crop_forward(_p(features), _p(grids), _p(out), B, C, H, W, N, oh, ow, _stream()),
+              "i2v_roi_crop_forward")
+    return out
+
+
+def roi_crop_backward(grad_out, grids, feat_shape):
+    """RoICropFunction.backward (functions/roi_crop.py:18-24): the gradient of the features [B,C,H,W] (the gradient of the
+    grids is zero in the reference)."""
+    grad_out, grids = _f32(grad_out, "grad_out"), _f32(grids, "grids")
+    B, C, H, W = (int(v) for v in feat_shape)
+    N, oh, ow, _ = grids.shape
+    if grad_out.shape != (N, C, oh, ow):
+        raise _lib.I2VError(f"roi_crop_backward: grad_out {tuple(grad_out.shape)} != {(N, C, oh, ow)}")
+    gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(load().i2v_roi_crop_backward(_p(grad_out), _p(grids), _p(gin), B, C, H, W, N, oh, ow, _stream()),
+              "i2v_roi_crop_backward")
+    return gin
+
+
 def pair_build(boxes, im_h: float, im_w: float, margin: float = 10.0, want_masks: bool = True):
     """boxes [N,4] -> (ixs [P], ixo [P] int64, rel_boxes [P,5], masks [P,2,32,32] or None), P = N(N-1)."""
     boxes = _f32(boxes, "boxes")

@@ -120,6 +120,29 @@ int i2v_c_roi_align_backward(const float* grad_out, const float* rois, float* gr
                              int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
                              int sampling_ratio, cudaStream_t stream);
 
+/* ---- 4b. roi_crop: the bilinear sampler of lib/model/roi_crop (functions/roi_crop.py:8-24) ---------------------- */
+/* Replace lib/model/roi_crop/src/roi_crop_cuda_kernel.h:6-34 (impl. roi_crop_cuda_kernel.cu:200-335), argument for
+ * argument as roi_crop_cuda.c:21-44,58-95 passes them: sizes, then per tensor the data pointer and its strides in
+ * elements (batch, channel, height, width; grids: batch, yx, height, width).  input [B,C,H,W]; grids [N,oh,ow,2] =
+ * (y, x) in [-1,1]; RoI n samples frame n / (N / B).  Return 1 = ok, 0 = error (the reference prints and returns 0).
+ * The backward ADDS into the caller-zeroed gradInputImages and leaves gradGrids untouched, like the reference
+ * (roi_crop_cuda_kernel.cu:155-193 computes the grid dot products and drops them). */
+int BilinearSamplerBHWD_updateOutput_cuda_kernel(int oc, int ow, int oh, int ob, int ic, int ih, int iw, int ib,
+                                                 float* inputImages, int isb, int isc, int ish, int isw, float* grids,
+                                                 int gsb, int gsc, int gsh, int gsw, float* output, int osb, int osc,
+                                                 int osh, int osw, cudaStream_t stream);
+int BilinearSamplerBHWD_updateGradInput_cuda_kernel(int goc, int gow, int goh, int gob, int ic, int ih, int iw, int ib,
+                                                    float* inputImages, int isb, int isc, int ish, int isw, float* grids,
+                                                    int gsb, int gsc, int gsh, int gsw, float* gradInputImages, int gisb,
+                                                    int gisc, int gish, int gisw, float* gradGrids, int ggsb, int ggsc,
+                                                    int ggsh, int ggsw, float* gradOutput, int gosb, int gosc, int gosh,
+                                                    int gosw, cudaStream_t stream);
+/* The same on contiguous tensors with status codes: out [N,C,oh,ow]; grad_in [B,C,H,W] is OVERWRITTEN. */
+int i2v_roi_crop_forward(const float* features, const float* grids, float* out, int batch, int channels, int height,
+                         int width, int num_rois, int out_h, int out_w, cudaStream_t stream);
+int i2v_roi_crop_backward(const float* grad_out, const float* grids, float* grad_in, int batch, int channels, int height,
+                          int width, int num_rois, int out_h, int out_w, cudaStream_t stream);
+
 /* ---- 5. NMS (nms_wrapper.py:13-21 -> nms_cpu.py:6-34; bit-exact keep lists) ------------------ */
 size_t i2v_nms_workspace_bytes(int batch, int num_boxes);
 /* `batch` independent sets of `num_boxes` rows (row stride `box_stride` floats, x1,y1,x2,y2 first), each

@@ -181,6 +181,29 @@ def c_roi_pool_backward(grad_out, rois, argmax, feat_shape, ph: int, pw: int):
     return out
 
 
+# ----------------------------------------------------------------------------- roi_crop
+def roi_crop_forward(feat, grids) -> np.ndarray:
+    """RoICropFunction.forward (functions/roi_crop.py:8-16 -> roi_crop_cuda_kernel.cu:47-108): feat [B,C,H,W], grids
+    [N,oh,ow,2] = (y, x) in [-1,1] -> [N,C,oh,ow]."""
+    feat, grids = _f32(feat), _f32(grids)
+    B, C, H, W = feat.shape
+    N, oh, ow, _ = grids.shape
+    out = np.empty((N, C, oh, ow), np.float32)
+    lib().orc_roi_crop_forward(_ptr(feat), _ptr(grids), _i(B), _i(C), _i(H), _i(W), _i(N), _i(oh), _i(ow), _ptr(out))
+    return out
+
+
+def roi_crop_backward(grad_out, grids, feat_shape) -> np.ndarray:
+    """RoICropFunction.backward (functions/roi_crop.py:18-24 -> roi_crop_cuda_kernel.cu:111-195): the gradient of the
+    features; the reference leaves the gradient of the grids at zero."""
+    grad_out, grids = _f32(grad_out), _f32(grids)
+    B, C, H, W = feat_shape
+    N, oh, ow, _ = grids.shape
+    out = np.empty((B, C, H, W), np.float32)
+    lib().orc_roi_crop_backward(_ptr(grad_out), _ptr(grids), _i(B), _i(C), _i(H), _i(W), _i(N), _i(oh), _i(ow), _ptr(out))
+    return out
+
+
 # ----------------------------------------------------------------------------- NMS
 def nms_sorted(boxes, thresh: float, max_keep: int = 0) -> np.ndarray:
     """Greedy NMS over rows already in descending-score order (nms_cpu.py:14-32 arithmetic)."""

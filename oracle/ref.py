@@ -95,6 +95,18 @@ def cpu_roi_pooling_forward_nhwc(feat_nhwc, rois, ph, pw, scale) -> np.ndarray:
     return out
 
 
+def cpu_roi_crop_forward_bhwd(feat_bhwc, grids) -> np.ndarray:
+    """roi_crop.c:7-103 `BilinearSamplerBHWD_updateOutput`: the CPU twin samples image b with grid b (no RoIs-per-image
+    division) from a channel-last tensor: feat [B,H,W,C], grids [B,oh,ow,2] -> [B,oh,ow,C]."""
+    feat = np.ascontiguousarray(feat_bhwc, np.float32)
+    grids = np.ascontiguousarray(grids, np.float32)
+    out = np.zeros((grids.shape[0], grids.shape[1], grids.shape[2], feat.shape[3]), np.float32)
+    tf, tg, to = _th(feat), _th(grids), _th(out)
+    rc = _cpu_lib().BilinearSamplerBHWD_updateOutput(ctypes.byref(tf), ctypes.byref(tg), ctypes.byref(to))
+    assert rc == 1
+    return out
+
+
 # ------------------------------------------------------------------ reference CUDA kernels (unmodified)
 _cuda = None
 
@@ -129,6 +141,36 @@ def cuda_roi_align_backward(top_diff, rois, feat_shape, gh, gw, scale):
     _cuda_lib().ROIAlignBackwardLaucher(_vp(top_diff.data_ptr()), _f(scale), _i(B), _i(rois.shape[0]), _i(H), _i(W),
                                         _i(C), _i(gh), _i(gw), _vp(rois.data_ptr()), _vp(gin.data_ptr()), _stream())
     return gin
+
+
+def cuda_roi_crop_forward(feat, grids):
+    """BilinearSamplerBHWD_updateOutput_cuda_kernel (roi_crop_cuda_kernel.cu:200-253) with the arguments of
+    roi_crop_cuda.c:21-44 on contiguous torch CUDA tensors; the output is pre-zeroed like functions/roi_crop.py:11."""
+    import torch
+    B, C, H, W = feat.shape
+    N, oh, ow, _ = grids.shape
+    out = torch.zeros((N, C, oh, ow), device=feat.device, dtype=torch.float32)
+    rc = _cuda_lib().BilinearSamplerBHWD_updateOutput_cuda_kernel(
+        _i(C), _i(ow), _i(oh), _i(N), _i(C), _i(H), _i(W), _i(B), _vp(feat.data_ptr()), _i(C * H * W), _i(H * W), _i(W), _i(1),
+        _vp(grids.data_ptr()), _i(oh * ow * 2), _i(1), _i(ow * 2), _i(2), _vp(out.data_ptr()), _i(C * oh * ow), _i(oh * ow),
+        _i(ow), _i(1), _stream())
+    assert rc == 1
+    return out
+
+
+def cuda_roi_crop_backward(feat, grids, grad_out):
+    """BilinearSamplerBHWD_updateGradInput_cuda_kernel (roi_crop_cuda_kernel.cu:255-335) -> (grad_input, grad_grids)."""
+    import torch
+    B, C, H, W = feat.shape
+    N, oh, ow, _ = grids.shape
+    gi, gg = torch.zeros_like(feat), torch.zeros_like(grids)
+    rc = _cuda_lib().BilinearSamplerBHWD_updateGradInput_cuda_kernel(
+        _i(C), _i(ow), _i(oh), _i(N), _i(C), _i(H), _i(W), _i(B), _vp(feat.data_ptr()), _i(C * H * W), _i(H * W), _i(W), _i(1),
+        _vp(grids.data_ptr()), _i(oh * ow * 2), _i(1), _i(ow * 2), _i(2), _vp(gi.data_ptr()), _i(C * H * W), _i(H * W), _i(W),
+        _i(1), _vp(gg.data_ptr()), _i(oh * ow * 2), _i(1), _i(ow * 2), _i(2), _vp(grad_out.data_ptr()), _i(C * oh * ow),
+        _i(oh * ow), _i(ow), _i(1), _stream())
+    assert rc == 1
+    return gi, gg
 
 
 def cuda_roi_pool_forward(feat, rois, ph, pw, scale):

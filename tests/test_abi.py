@@ -17,7 +17,8 @@ def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src)
-    return [n for n in names if n.startswith("i2v_") or n.endswith("Laucher") or n == "nms_cuda_compute"]
+    return [n for n in names if n.startswith("i2v_") or n.endswith("Laucher") or n == "nms_cuda_compute" or
+            n.startswith("BilinearSamplerBHWD_")]
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +32,8 @@ def lib():
 def test_header_declares_the_reference_launchers():
     names = _declared()
     for n in ("ROIAlignForwardLaucher", "ROIAlignBackwardLaucher", "ROIPoolForwardLaucher", "ROIPoolBackwardLaucher",
-              "nms_cuda_compute"):
+              "nms_cuda_compute", "BilinearSamplerBHWD_updateOutput_cuda_kernel",
+              "BilinearSamplerBHWD_updateGradInput_cuda_kernel"):
         assert n in names
     assert len(names) == len(set(names)) and len(names) >= 24
 

@@ -10,6 +10,7 @@ from i2vsgg_b200 import synth
 from oracle import oracle, ref
 
 SCALE = 1.0 / 16
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def test_anchor_table(golden):
@@ -180,3 +181,33 @@ def test_pair_stage_matches_python_loops():
 def test_live_reference_python_agrees_with_golden(golden):
     dets = synth.nms_dets(3, 300)
     assert np.array_equal(ref.py_nms_cpu(dets, 0.7), golden["nms_keep_3_300_0.7"])
+
+
+def test_roi_crop_forward_bit_exact_vs_reference_c():
+    """oracle.roi_crop_forward against the reference's roi_crop.c executed (tests/golden/make_roi_crop_golden.py): one RoI
+    per image, where the CPU file and the CUDA kernel the oracle follows describe the same sampling."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_roi_crop_golden", os.path.join(HERE, "golden", "make_roi_crop_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    feat, grids = mod.crop_inputs()
+    want = np.load(os.path.join(HERE, "golden", "roi_crop_golden.npz"))["forward"]
+    assert np.array_equal(oracle.roi_crop_forward(feat, grids), want)
+    if ref.have_cpu_ref():
+        live = ref.cpu_roi_crop_forward_bhwd(feat.transpose(0, 2, 3, 1), grids).transpose(0, 3, 1, 2)
+        assert np.array_equal(live, want)
+
+
+def test_roi_crop_backward_is_adjoint_of_forward_and_rois_per_image():
+    rng = np.random.default_rng(12)
+    B, C, H, W, per = 2, 3, 9, 14, 4
+    feat = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    grids = rng.uniform(-1.2, 1.2, (B * per, 5, 6, 2)).astype(np.float32)
+    g = rng.standard_normal((B * per, C, 5, 6)).astype(np.float32)
+    out = oracle.roi_crop_forward(feat, grids)
+    gin = oracle.roi_crop_backward(g, grids, feat.shape)
+    lhs, rhs = float((out.astype(np.float64) * g).sum()), float((feat.astype(np.float64) * gin).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    # RoI n samples frame n // per (roi_crop_cuda_kernel.cu:65): frame 1's RoIs do not see frame 0
+    alone = oracle.roi_crop_forward(feat[1:], grids[per:])
+    assert np.array_equal(out[per:], alone)
