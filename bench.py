@@ -462,7 +462,22 @@ def projection_side_measurement(dev):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-    return {"kernel": "linear_tcgen05_pair_kernel, cta_group::2 (fc6 of vrd.forward, SURVEY 8 a19)", "shape": [m, n, k], "dtype": "bf16",
+    # the same GEMM on fp32 operands (tcgen05 kind::tf32), what vrd(..., precision="tf32") runs
+    x32, w32 = x.float(), w.float()
+    y32 = torch.empty((m, n), device=dev, dtype=torch.float32)
+    for _ in range(2):
+        ops.linear(x32, w32, b, relu=True, out=y32)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(5):
+        ops.linear(x32, w32, b, relu=True, out=y32)
+    e.record()
+    torch.cuda.synchronize()
+    ms32 = s.elapsed_time(e) / 5
+    tf32 = {"dtype": "tf32 (fp32 operands)", "ms": ms32, "tflops": 2.0 * m * n * k / (ms32 * 1e-3) / 1e12,
+            "note": "no measured tf32 peak in MEASURED_PEAKS.json; nominal dense tf32 is half the bf16 rate"}
+    del x32, w32, y32
+    return {"tf32": tf32, "kernel": "linear_tcgen05_pair_kernel, cta_group::2 (fc6 of vrd.forward, SURVEY 8 a19)", "shape": [m, n, k], "dtype": "bf16",
             "ms": ms, "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(peaks_path)
                                    else "fallback (B200_PROFILING.md)"}}

@@ -55,8 +55,11 @@ SIGNATURES = {
     "i2v_triplet_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "i2v_roi_pool_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _ll, _i, _vp]),
     "i2v_linear_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _vp]),
+    "i2v_round_tf32": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp]),
+    "i2v_linear_forward_dropout": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _f, _vp]),
     "i2v_cast_bf16": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp]),
     "i2v_im2col_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "i2v_im2col_f32": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _ll, _vp]),
     "i2v_pair_rows_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
     "i2v_conv2d_nhwc_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _i, _i, _vp]),
     "i2v_pair_conv1_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

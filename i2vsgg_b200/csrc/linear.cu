@@ -121,9 +121,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 
 // Accumulator rows -> y: warp quarter q owns TMEM lanes [32 q, +32) = tile rows; 32 columns per tcgen05.ld.
+// `mask` (optional, [M, N] bytes, pitch ldm): inverted dropout behind the activation -- y = mask ? y * mscale : 0, the
+// F.dropout(x, training=True) of resnet_SGG_emb.py:148-151 with the keep mask drawn by the caller.
+struct DropMask {
+    const unsigned char* mask = nullptr;
+    long long ldm = 0;
+    float scale = 1.f;
+};
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int q, int lane, int row, int n0, const float* __restrict__ bias,
-                                              void* __restrict__ y, int M, int N, long long ldy, int y_bf16, int relu) {
+                                              void* __restrict__ y, int M, int N, long long ldy, int y_bf16, int relu,
+                                              const DropMask dm = DropMask{}) {
         const bool vec_ok = y_bf16 ? ((ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
                                    : ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
 #pragma unroll 1
@@ -139,6 +147,12 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int q, int lan
                     float t = __uint_as_float(v[j]);
                     if (bias != nullptr && col0 + j < N) t += __ldg(bias + col0 + j);
                     f[j] = relu ? fmaxf(t, 0.f) : t;
+                }
+                if (dm.mask != nullptr) {
+                    const unsigned char* mrow = dm.mask + (size_t)row * dm.ldm + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < N) f[j] = __ldg(mrow + j) ? f[j] * dm.scale : 0.f;
                 }
                 if (y_bf16) {
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * ldy + col0;
@@ -187,7 +201,7 @@ template <int KIND, int BN, bool CONV = false>
 __global__ void __launch_bounds__(kThreads, 1)
     linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                           const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
-                          int y_bf16, int relu, ConvGeom cg = ConvGeom{}) {
+                          int y_bf16, int relu, ConvGeom cg = ConvGeom{}, const DropMask dm = DropMask{}) {
     constexpr int ELEMS = (KIND == 0) ? 64 : 32;
     constexpr int kBN = Tile<BN>::kBN, kStages = Tile<BN>::kStages, kStageBytes = Tile<BN>::kStageBytes;
     constexpr int kTmemCols = Tile<BN>::kTmemCols;
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum, 0);
         tc_fence_after();
-        epilogue_rows<kBN>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu);
+        epilogue_rows<kBN>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu, dm);
     }
     tc_fence_before();
     __syncthreads();
@@ -314,7 +328,7 @@ template <int KIND, int kPairStages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     linear_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
-                               int y_bf16, int relu) {
+                               int y_bf16, int relu, const DropMask dm) {
     constexpr int ELEMS = (KIND == 0) ? 64 : 32;
     constexpr uint32_t FMT = (KIND == 0) ? 1u : 2u;
     // D = fp32, A/B format, K-major, N = 256 (>> 3), M = 256 (>> 4)
@@ -410,7 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum, 0);
         tc_fence_after();
-        epilogue_rows<256>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu);
+        epilogue_rows<256>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu, dm);
     }
     tc_fence_before();
     __syncthreads();
@@ -567,9 +581,9 @@ int make_map(CUtensorMap* map, const void* base, int kind, int64_t rows, int64_t
 
 using namespace i2v;
 
-extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
-                                  long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
-                                  cudaStream_t stream) {
+static int linear_impl(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, long long ldx,
+                       long long ldw, long long ldy, int in_dtype, int out_dtype, int relu, const DropMask dm,
+                       cudaStream_t stream) {
     I2V_REQUIRE(M >= 0 && N >= 0 && K >= 1, "linear_forward: bad shape %d x %d x %d", M, N, K);
     I2V_REQUIRE(in_dtype == I2V_DT_BF16 || in_dtype == I2V_DT_TF32, "linear_forward: in_dtype %d", in_dtype);
     I2V_REQUIRE(out_dtype == I2V_DT_BF16 || out_dtype == I2V_DT_F32, "linear_forward: out_dtype %d", out_dtype);
@@ -593,11 +607,11 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
         if (kind == 0) {
             auto kern = linear_tcgen05_pair_kernel<0, kPairStages>;
             I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
-            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu);
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm);
         } else {
             auto kern = linear_tcgen05_pair_kernel<1, kPairStages>;
             I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
-            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu);
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm);
         }
         return check_launch("linear_tcgen05_pair_kernel");
     }
@@ -608,7 +622,7 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
     do {                                                                                                              \
         auto kern = linear_tcgen05_kernel<KIND, BN>;                                                                  \
         I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BN>::kSmemBytes)); \
-        kern<<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb, relu, ConvGeom{}); \
+        kern<<<grid, kThreads, Tile<BN>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb, relu, ConvGeom{}, dm); \
     } while (0)
     if (kind == 0 && bn == 256) I2V_LAUNCH_LINEAR(0, 256);
     else if (kind == 0) I2V_LAUNCH_LINEAR(0, 128);
@@ -616,6 +630,23 @@ extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bia
     else I2V_LAUNCH_LINEAR(1, 128);
 #undef I2V_LAUNCH_LINEAR
     return check_launch("linear_tcgen05_kernel");
+}
+
+extern "C" int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                                  long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
+                                  cudaStream_t stream) {
+    return linear_impl(x, w, bias, y, M, N, K, ldx, ldw, ldy, in_dtype, out_dtype, relu, DropMask{}, stream);
+}
+
+extern "C" int i2v_linear_forward_dropout(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                                          long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
+                                          const unsigned char* keep_mask, long long ldm, float scale, cudaStream_t stream) {
+    I2V_REQUIRE(keep_mask && ldm >= N, "linear_forward_dropout: the keep mask is [M, N] bytes with pitch >= N");
+    DropMask dm;
+    dm.mask = keep_mask;
+    dm.ldm = ldm;
+    dm.scale = scale;
+    return linear_impl(x, w, bias, y, M, N, K, ldx, ldw, ldy, in_dtype, out_dtype, relu, dm, stream);
 }
 
 extern "C" int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, long long lds, long long ldd,
@@ -711,6 +742,6 @@ extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float
     auto kern = linear_tcgen05_kernel<0, 128, true>;
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<128>::kSmemBytes));
     kern<<<grid, kThreads, Tile<128>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, out_channels, K, ldy,
-                                                           out_dtype == I2V_DT_BF16, relu, cg);
+                                                           out_dtype == I2V_DT_BF16, relu, cg, DropMask{});
     return check_launch("linear_tcgen05_kernel<conv>");
 }

@@ -15,8 +15,11 @@ __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162f
 // out[(n*OH + oy)*OW + ox][(ky*KW + kx)*C + c] = in[n, c, oy*stride - pad + ky, ox*stride - pad + kx] (0 outside),
 // columns [KH*KW*C, ldo) are zero-filled so the row pitch can be padded to the TMA's 16-byte rule.
 // `in` is addressed through element strides (sn, sc, sy, sx): NCHW fp32 masks and NHWC bf16 activations both fit.
-template <typename InT>
-__global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__device__ __forceinline__ void put_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void put_out(float* p, float v) { *p = v; }
+
+template <typename InT, typename OutT = __nv_bfloat16>
+__global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in, OutT* __restrict__ out,
                                                      int64_t total, int C, int H, int W, int64_t sn, int64_t sc,
                                                      int64_t sy, int64_t sx, int KH, int KW, int stride, int pad, int OH,
                                                      int OW, int64_t ldo) {
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const InT* __restrict__ in,
             int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
             if (y >= 0 && y < H && x >= 0 && x < W) v = to_float(in[n * sn + c * sc + y * sy + x * sx]);
         }
-        out[idx] = __float2bfloat16_rn(v);
+        put_out(out + idx, v);
     }
 }
 
@@ -230,6 +233,53 @@ extern "C" int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels
                                                                width, stride_n, stride_c, stride_y, stride_x, kernel_h,
                                                                kernel_w, stride, pad, OH, OW, ldo);
     return check_launch("im2col_kernel");
+}
+
+// fp32 -> the nearest tf32 value (10 mantissa bits), kept in an fp32 word.  tcgen05 kind::tf32 reads the upper 19 bits of
+// its operands, i.e. it TRUNCATES; rounding the operands first removes the systematic shrink of every product (about
+// 1e-3 per layer, which six layers of the relation head turned into 4e-3 of the feature scale).
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows,
+                                                         int64_t cols, int64_t lds, int64_t ldd) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(src[r * lds + c]));
+        dst[r * ldd + c] = __uint_as_float(u);
+    }
+}
+extern "C" int i2v_round_tf32(const float* src, float* dst, long long rows, long long cols, long long lds, long long ldd,
+                              cudaStream_t stream) {
+    I2V_REQUIRE(rows >= 0 && cols >= 0 && lds >= cols && ldd >= cols, "round_tf32: bad shape");
+    if (rows == 0 || cols == 0) return I2V_OK;
+    I2V_REQUIRE(src && dst, "round_tf32: null pointer");
+    round_tf32_kernel<<<grid_for(rows * cols, 256), 256, 0, stream>>>(src, dst, rows, cols, lds, ldd);
+    return check_launch("round_tf32_kernel");
+}
+
+// The same patches as fp32 rows (the tf32 precision of the relation head): fp32 or bf16 input, any strides.
+extern "C" int i2v_im2col_f32(const void* in, int in_dtype, int n, int channels, int height, int width, long long stride_n,
+                              long long stride_c, long long stride_y, long long stride_x, int kernel_h, int kernel_w,
+                              int stride, int pad, float* out, long long ldo, cudaStream_t stream) {
+    I2V_REQUIRE(n >= 0 && channels >= 1 && height >= 1 && width >= 1 && kernel_h >= 1 && kernel_w >= 1 && stride >= 1 &&
+                    pad >= 0,
+                "im2col: bad shape");
+    I2V_REQUIRE(in_dtype == I2V_DT_F32 || in_dtype == I2V_DT_BF16, "im2col: in_dtype %d", in_dtype);
+    int OH = (height + 2 * pad - kernel_h) / stride + 1, OW = (width + 2 * pad - kernel_w) / stride + 1;
+    I2V_REQUIRE(OH >= 1 && OW >= 1, "im2col: kernel larger than the padded input");
+    I2V_REQUIRE(ldo >= (long long)kernel_h * kernel_w * channels, "im2col: row pitch smaller than a patch");
+    int64_t total = (int64_t)n * OH * OW * ldo;
+    if (total == 0) return I2V_OK;
+    I2V_REQUIRE(in && out, "im2col: null pointer");
+    int grid = grid_for(total, 256, 16);
+    if (in_dtype == I2V_DT_F32)
+        im2col_kernel<float, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), out, total, channels, height, width,
+                                                              stride_n, stride_c, stride_y, stride_x, kernel_h, kernel_w,
+                                                              stride, pad, OH, OW, ldo);
+    else
+        im2col_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, total,
+                                                                      channels, height, width, stride_n, stride_c, stride_y,
+                                                                      stride_x, kernel_h, kernel_w, stride, pad, OH, OW, ldo);
+    return check_launch("im2col_kernel<f32>");
 }
 
 extern "C" int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,

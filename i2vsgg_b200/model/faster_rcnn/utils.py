@@ -1,6 +1,10 @@
 """`Conv2d` and `FC` of lib/model/faster_rcnn/utils.py:32-60: parameter containers with the reference's names
 (`.conv`, `.bn`, `.fc`), so a reference checkpoint loads with `load_state_dict`.  Their `forward` runs on the
-sm_100a kernels of this package: bf16 tensor-core operands, fp32 accumulation."""
+sm_100a kernels of this package: bf16 tensor-core operands (or tf32 for fp32 inputs), fp32 accumulation.
+
+The derived copies of the weights (bf16 / padded / folded BatchNorm) are rebuilt whenever a parameter's version
+counter, data pointer or device changes: an optimizer step, `load_state_dict` or `.to()` after the first forward can
+not leave a stale copy behind."""
 from __future__ import annotations
 
 import torch
@@ -15,9 +19,16 @@ class FC(nn.Module):
         self.fc = nn.Linear(in_features, out_features)
         self.relu = nn.ReLU(inplace=True) if relu else None
         self._w = None
+        self._key = None
+
+    def _state(self):
+        w, b = self.fc.weight, self.fc.bias
+        return (w._version, w.data_ptr(), b._version, b.data_ptr(), str(w.device))
 
     def prepare(self):
         """(Re)builds the bf16 copy of the weight the tensor cores read; the row pitch is padded to 16 bytes."""
+        self._key = self._state()
+        self._w32 = None
         w = self.fc.weight.detach()
         k = w.size(1)
         kp = (k + 7) // 8 * 8
@@ -27,11 +38,26 @@ class FC(nn.Module):
         self._b = self.fc.bias.detach().float().contiguous()
         return self
 
-    def forward(self, x, out=None, out_dtype=torch.bfloat16):
-        """x [M, in_features] bf16 (rows may be strided) -> [M, out_features]; `out` may be a column slice."""
-        if self._w is None or self._w.device != x.device:
+    def forward(self, x, out=None, out_dtype=None, keep_mask=None, keep_scale=1.0):
+        """x [M, in_features] (rows may be strided) -> [M, out_features]; `out` may be a column slice.  bf16 rows go
+        through the bf16 copy of the weight (tcgen05 kind::f16), fp32 rows through the fp32 weight itself (kind::tf32).
+        `keep_mask` [M, out_features] uint8: dropout behind the activation, applied in the kernel's epilogue."""
+        if self._w is None or self._key != self._state():
             self.prepare()
-        return ops.linear(x, self._w, self._b, relu=self.relu is not None, out=out, out_dtype=out_dtype)
+        if x.dtype == torch.float32:
+            if self._w32 is None:
+                w = self.fc.weight.detach().float().clone().contiguous()     # a copy: the parameter itself stays fp32
+                if (w.size(1) * 4) % 16:                       # TMA: 16-byte row pitch
+                    kp = (w.size(1) + 3) // 4 * 4
+                    buf = torch.zeros((w.size(0), kp), dtype=torch.float32, device=w.device)
+                    buf[:, : w.size(1)] = w
+                    w = buf[:, : self.fc.in_features]
+                self._w32 = ops.round_tf32(w, w)           # the tensor core truncates: round the operands first
+            x = ops.round_tf32(x)                          # out of place: the caller's activations are left alone
+            return ops.linear(x, self._w32, self._b, relu=self.relu is not None, out=out,
+                              out_dtype=out_dtype or torch.float32, keep_mask=keep_mask, keep_scale=keep_scale)
+        return ops.linear(x, self._w, self._b, relu=self.relu is not None, out=out, out_dtype=out_dtype or torch.bfloat16,
+                          keep_mask=keep_mask, keep_scale=keep_scale)
 
 
 class Conv2d(nn.Module):
@@ -42,10 +68,23 @@ class Conv2d(nn.Module):
         self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0, affine=True) if bn else None
         self.relu = nn.ReLU(inplace=True) if relu else None
         self._w = None
+        self._key = None
+
+    def _state(self):
+        ps = [self.conv.weight, self.conv.bias]
+        if self.bn is not None:
+            ps += [self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var]
+        return tuple((p._version, p.data_ptr()) for p in ps) + (str(self.conv.weight.device), self.training)
+
+    def _fresh(self):
+        if self._w is None or self._key != self._state():
+            self.prepare()
 
     def prepare(self):
         """Weight as [out, (ky, kx, c)] bf16 rows (the patch order of `ops.im2col_bf16`), eval-mode BatchNorm folded
         into weight and bias (utils.py:43-44 in eval mode is an affine map per output channel)."""
+        self._key = self._state()
+        self._w32 = None
         w = self.conv.weight.detach().float()
         b = self.conv.bias.detach().float()
         if self.bn is not None:
@@ -71,8 +110,7 @@ class Conv2d(nn.Module):
         """This layer applied to P two-channel inputs whose channels are `obj_x[ixs[p]]` and `obj_x[ixo[p]]`
         (obj_x [N,H,W]): the convolution is linear in its input channels, so each OBJECT map is convolved once with
         either half of the kernel and a pair is the sum of two rows plus the bias.  -> NHWC bf16 [P,OH,OW,out]."""
-        if self._w is None or self._w.device != obj_x.device:
-            self.prepare()
+        self._fresh()
         o, kh = self.conv.out_channels, self.conv.kernel_size[0]
         if self.conv.in_channels != 2:
             raise ValueError("forward_pairs needs a two-channel convolution")
@@ -91,10 +129,33 @@ class Conv2d(nn.Module):
         y = ops.pair_conv1_bf16(maps.view(n, oh * ow, 2 * o), ixs, ixo, self._b, relu=self.relu is not None)
         return y.view(ixs.numel(), oh, ow, o)
 
+    def forward_tf32(self, x, layout: str):
+        """The layer on fp32 patches and fp32 weights through tcgen05 kind::tf32 (`vrd(..., precision="tf32")`):
+        x fp32, [N,C,H,W] or [N,H,W,C] -> NHWC fp32 [N,OH,OW,out]."""
+        self._fresh()
+        kh = self.conv.kernel_size[0]
+        if getattr(self, "_w32", None) is None:
+            w = self.conv.weight.detach().float()
+            b = self.conv.bias.detach().float()
+            if self.bn is not None:
+                sc = self.bn.weight.detach().float() / torch.sqrt(self.bn.running_var.float() + self.bn.eps)
+                w = w * sc[:, None, None, None]
+                b = (b - self.bn.running_mean.float()) * sc + self.bn.bias.detach().float()
+            o, c = w.size(0), w.size(1)
+            k = kh * kh * c
+            kp = (k + 3) // 4 * 4
+            buf = torch.zeros((o, kp), dtype=torch.float32, device=w.device)
+            buf[:, :k] = w.permute(0, 2, 3, 1).reshape(o, k)
+            self._w32, self._kp32, self._b32 = ops.round_tf32(buf, buf), kp, b.contiguous()
+        patches, (n, oh, ow) = ops.im2col_bf16(x.float().contiguous(), kh, self.conv.stride[0], self.conv.padding[0], layout,
+                                               ld=self._kp32, out_dtype=torch.float32)
+        ops.round_tf32(patches, patches)
+        y = ops.linear(patches, self._w32, self._b32, relu=self.relu is not None, out_dtype=torch.float32)
+        return y.view(n, oh, ow, self.conv.out_channels)
+
     def forward(self, x, layout: str):
         """x [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`'nhwc'`) -> NHWC bf16 [N,OH,OW,out]: im2col rows + one FC launch."""
-        if self._w is None or self._w.device != x.device:
-            self.prepare()
+        self._fresh()
         kh = self.conv.kernel_size[0]
         st, pd = self.conv.stride[0], self.conv.padding[0]
         if layout == "nhwc" and x.dtype == torch.bfloat16 and x.is_contiguous() and st > 1:

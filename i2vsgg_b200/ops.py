@@ -355,9 +355,10 @@ def roi_pool_rows(features, rois, pooled_h: int, pooled_w: int, spatial_scale: f
     return out
 
 
-def linear(x, weight, bias=None, relu: bool = False, out=None, out_dtype=torch.float32):
+def linear(x, weight, bias=None, relu: bool = False, out=None, out_dtype=torch.float32, keep_mask=None, keep_scale: float = 1.0):
     """FC of lib/model/faster_rcnn/utils.py:48-60 on tcgen05: act(x @ weight.T + bias).  x [M,K] and weight [N,K] are both bf16
-    (tensor cores in bf16) or both fp32 (tensor cores in tf32); rows may be strided.  `out` may be a column slice."""
+    (tensor cores in bf16) or both fp32 (tensor cores in tf32); rows may be strided.  `out` may be a column slice.
+    `keep_mask` [M,N] uint8 applies inverted dropout in the epilogue: y = keep ? y * keep_scale : 0."""
     if not (x.is_cuda and weight.is_cuda) or x.dtype != weight.dtype or x.dtype not in _TORCH_DT:
         raise _lib.I2VError("linear: x and weight must be CUDA tensors, both bf16 or both fp32")
     if x.dim() != 2 or weight.dim() != 2 or x.size(1) != weight.size(1) or x.stride(1) != 1 or weight.stride(1) != 1:
@@ -374,9 +375,29 @@ def linear(x, weight, bias=None, relu: bool = False, out=None, out_dtype=torch.f
             raise _lib.I2VError("linear: bias size")
     in_dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_TF32
     with torch.cuda.device(x.device):
-        check(load().i2v_linear_forward(_p(x), _p(weight), _p(bias), _p(out), M, N, K, x.stride(0), weight.stride(0),
-                                        out.stride(0), in_dt, _TORCH_DT[out.dtype], int(bool(relu)), _stream()),
-              "i2v_linear_forward")
+        if keep_mask is not None:
+            if keep_mask.dtype != torch.uint8 or keep_mask.shape != (M, N) or keep_mask.stride(1) != 1 or not keep_mask.is_cuda:
+                raise _lib.I2VError("linear: keep_mask must be a [M,N] uint8 CUDA tensor with contiguous rows")
+            check(load().i2v_linear_forward_dropout(_p(x), _p(weight), _p(bias), _p(out), M, N, K, x.stride(0), weight.stride(0),
+                                                    out.stride(0), in_dt, _TORCH_DT[out.dtype], int(bool(relu)),
+                                                    _p(keep_mask), keep_mask.stride(0), float(keep_scale), _stream()),
+                  "i2v_linear_forward_dropout")
+        else:
+            check(load().i2v_linear_forward(_p(x), _p(weight), _p(bias), _p(out), M, N, K, x.stride(0), weight.stride(0),
+                                            out.stride(0), in_dt, _TORCH_DT[out.dtype], int(bool(relu)), _stream()),
+                  "i2v_linear_forward")
+    return out
+
+
+def round_tf32(x, out=None):
+    """fp32 [rows, cols] (rows may be strided) -> the nearest tf32 values, as fp32 words (`out` may be `x`)."""
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1 or x.dtype != torch.float32:
+        raise _lib.I2VError("round_tf32: expected a 2-d fp32 CUDA tensor with contiguous rows")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().i2v_round_tf32(_p(x), _p(out), x.size(0), x.size(1), x.stride(0), out.stride(0), _stream()),
+              "i2v_round_tf32")
     return out
 
 
@@ -407,8 +428,8 @@ def rel_scores(x, prd, softmax: bool = True):
     return out
 
 
-def im2col_bf16(x, kernel: int, stride: int, pad: int, layout: str, ld: int | None = None):
-    """Patches of a square-kernel convolution as bf16 rows [(n, oy, ox), (ky, kx, c)] (pitch `ld`, zero padded).
+def im2col_bf16(x, kernel: int, stride: int, pad: int, layout: str, ld: int | None = None, out_dtype=torch.bfloat16):
+    """Patches of a square-kernel convolution as bf16 (or fp32) rows [(n, oy, ox), (ky, kx, c)] (pitch `ld`, zero padded).
     x is [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`layout='nhwc'`), fp32 or bf16, contiguous."""
     if not x.is_cuda or x.dim() != 4 or x.dtype not in _TORCH_DT or not x.is_contiguous():
         raise _lib.I2VError("im2col_bf16: expected a contiguous 4-d fp32/bf16 CUDA tensor")
@@ -423,10 +444,11 @@ def im2col_bf16(x, kernel: int, stride: int, pad: int, layout: str, ld: int | No
     oh, ow = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
     k = kernel * kernel * c
     ld = k if ld is None else int(ld)
-    out = torch.empty((n * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((n * oh * ow, ld), dtype=out_dtype, device=x.device)
     with torch.cuda.device(x.device):
-        check(load().i2v_im2col_bf16(_p(x), _TORCH_DT[x.dtype], n, c, h, w, sn, sc, sy, sx, kernel, kernel, stride, pad,
-                                     _p(out), ld, _stream()), "i2v_im2col_bf16")
+        fn = load().i2v_im2col_f32 if out_dtype == torch.float32 else load().i2v_im2col_bf16
+        check(fn(_p(x), _TORCH_DT[x.dtype], n, c, h, w, sn, sc, sy, sx, kernel, kernel, stride, pad, _p(out), ld, _stream()),
+              "i2v_im2col")
     return out, (n, oh, ow)
 
 

@@ -234,6 +234,12 @@ int i2v_roi_pool_rows(const float* features, const float* rois, void* out, int b
 int i2v_linear_forward(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
                        long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
                        cudaStream_t stream);
+/* The same with F.dropout(y, training=True) (resnet_SGG_emb.py:148-151) applied behind the activation in the epilogue:
+ * keep_mask [M,N] bytes (row pitch ldm >= N), y = keep ? y * scale : 0.  The caller draws the mask (torch's generator in
+ * the Python mirror) and passes scale = 1 / (1 - p). */
+int i2v_linear_forward_dropout(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                               long long ldx, long long ldw, long long ldy, int in_dtype, int out_dtype, int relu,
+                               const unsigned char* keep_mask, long long ldm, float scale, cudaStream_t stream);
 /* fp32 -> bf16 (round to nearest even) of a [rows, cols] matrix; pitches in elements. */
 int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, long long lds, long long ldd,
                   cudaStream_t stream);
@@ -243,6 +249,14 @@ int i2v_cast_bf16(const float* src, void* dst, long long rows, long long cols, l
 int i2v_im2col_bf16(const void* in, int in_dtype, int n, int channels, int height, int width, long long stride_n,
                     long long stride_c, long long stride_y, long long stride_x, int kernel_h, int kernel_w,
                     int stride, int pad, void* out, long long ldo, cudaStream_t stream);
+/* The same patches as fp32 rows (the tf32 precision of the relation head). */
+int i2v_im2col_f32(const void* in, int in_dtype, int n, int channels, int height, int width, long long stride_n,
+                   long long stride_c, long long stride_y, long long stride_x, int kernel_h, int kernel_w, int stride,
+                   int pad, float* out, long long ldo, cudaStream_t stream);
+/* fp32 [rows, cols] -> the nearest tf32 value in an fp32 word (in place allowed).  tcgen05 kind::tf32 truncates its
+ * operands; the tf32 path of the relation head rounds them first. */
+int i2v_round_tf32(const float* src, float* dst, long long rows, long long cols, long long lds, long long ldd,
+                   cudaStream_t stream);
 /* cat(index_select(obj, 0, ixs), index_select(obj, 0, ixo), 1) of resnet_SGG_emb.py:150-151,169 as bf16 rows
  * [P, 2E] with pitch ldo; obj [N,E] fp32, ixs/ixo [P] int64. */
 int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo, void* out, int num_obj,

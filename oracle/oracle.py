@@ -370,10 +370,13 @@ def _normalize(x):
 
 
 def vrd_forward(params: dict, prd_vecs, fmap, boxes, rel_boxes, spatial, ix1, ix2, use_obj_visual=True,
-                spatial_type=2, pool: int = 7, rows=None, nthreads: int = 1):
-    """vrd.forward in eval mode (resnet_SGG_emb.py:128-221) restated in numpy fp32 -> (scores [P,n_rel], feat [P,emb]).
+                spatial_type=2, pool: int = 7, rows=None, nthreads: int = 1, dropout_masks=None, dropout_p: float = 0.5):
+    """vrd.forward (resnet_SGG_emb.py:128-221) restated in numpy fp32 -> (scores [P,n_rel], feat [P,emb]).
 
-    roi_pool is the model._C flavour (`c_roi_pool_forward`); dropout is the identity in eval mode (:148-149).
+    roi_pool is the model._C flavour (`c_roi_pool_forward`).  Eval mode by default: dropout is the identity (:148-149)
+    and the scores are softmaxed (:215-219).  `dropout_masks` = the four keep masks of the F.dropout calls at :148, :149,
+    :162, :163 ([N,h], [N,h], [P,h], [P,h]) switches to TRAINING mode: y = keep * y / (1 - p) behind fc6 / fc7 of both
+    branches and raw cosine similarities as scores.
     `rows` restricts the computation to a subset of pair indices (full-size spot checks)."""
     fmap = _f32(fmap)
     boxes = _f32(boxes).reshape(-1, 5)
@@ -383,11 +386,15 @@ def vrd_forward(params: dict, prd_vecs, fmap, boxes, rel_boxes, spatial, ix1, ix
     if rows is not None:
         rows = np.asarray(rows, np.int64)
         rel_boxes, ix1, ix2, spatial = rel_boxes[rows], ix1[rows], ix2[rows], spatial[rows]
+    training = dropout_masks is not None
+    keep = [np.asarray(m, np.float32) * np.float32(1.0 / (1.0 - dropout_p)) for m in dropout_masks] if training else None
+    drop = (lambda y, k: y * keep[k]) if training else (lambda y, k: y)
     x_so, _ = c_roi_pool_forward(fmap, boxes, pool, pool, 1.0 / 16, nthreads)                    # :144
-    x_so = _fc(_fc(x_so.reshape(len(boxes), -1), params, "fc6.fc"), params, "fc7.fc")           # :146-149
+    x_so = drop(_fc(drop(_fc(x_so.reshape(len(boxes), -1), params, "fc6.fc"), 0), params, "fc7.fc"), 1)   # :146-149
     obj = _fc(x_so, params, "so_vis_embeddings.fc", relu=False)                                 # :150
     x_u, _ = c_roi_pool_forward(fmap, rel_boxes, pool, pool, 1.0 / 16, nthreads)                 # :158
-    x = _fc(_fc(_fc(x_u.reshape(len(rel_boxes), -1), params, "fc6.fc"), params, "fc7.fc"), params, "fc8.fc")  # :160-164
+    x = drop(_fc(drop(_fc(x_u.reshape(len(rel_boxes), -1), params, "fc6.fc"), 2), params, "fc7.fc"), 3)   # :160-163
+    x = _fc(x, params, "fc8.fc")                                                                # :164
     parts = [x]
     if use_obj_visual:                                                                          # :166-170
         parts.append(_fc(np.concatenate([obj[ix1], obj[ix2]], 1), params, "fc_so.fc"))
@@ -403,5 +410,7 @@ def vrd_forward(params: dict, prd_vecs, fmap, boxes, rel_boxes, spatial, ix1, ix
     prd = np.where(prd > 0, prd, np.float32(0.1) * prd)
     prd = prd @ params["prd_sem_embeddings.2.weight"].T + params["prd_sem_embeddings.2.bias"]
     sim = (_normalize(x) @ _normalize(prd).T).astype(np.float64)                                # :207-211
+    if training:                                                                                # :215: no softmax
+        return sim.astype(np.float32), x
     e = np.exp(sim - sim.max(1, keepdims=True))                                                 # :216-219 (eval)
     return (e / e.sum(1, keepdims=True)).astype(np.float32), x

@@ -1,4 +1,3 @@
 #!/bin/bash
-# whole GPU suite + the config-3 frame timing
-python -m pytest tests -x -q -m gpu 2>&1 | tail -15
-python profiles/run_vrd.py 2>&1 | tail -5
+# whole GPU suite
+python -m pytest tests -x -q -m gpu -s 2>&1 | grep -v "^$" | tail -25

@@ -189,15 +189,75 @@ def test_vrd_object_mask_path_matches_pair_mask_path(orc):
     assert float((a - b).abs().max()) <= 2 ** -7 * float(a.abs().max())
 
 
-def test_vrd_refuses_training_mode_and_cpu():
+def test_vrd_refuses_cpu_parameters():
     from i2vsgg_b200.model.faster_rcnn.resnet_SGG_emb import vrd
     args = synth.VrdArgs(vrd_in_channels=16, vrd_hidden=64)
     net = vrd(args, None, synth.prd_vectors(1))
-    with pytest.raises(NotImplementedError):
-        net.train()(None, None, None, None, None, None, None)
     with pytest.raises(RuntimeError):
         net.eval()(np.zeros((1, 16, 38, 63), np.float32), np.zeros((2, 5)), np.zeros((2, 5)), np.zeros((2, 2, 32, 32)),
                    [1, 1], [0, 1], [1, 0])
+
+
+def test_vrd_training_mode_dropout_and_raw_scores(orc):
+    """train(): inverted dropout (p = 0.5) behind fc6 / fc7 of both branches (resnet_SGG_emb.py:148-149, :161-163), applied in
+    the FC epilogue, and raw cosine similarities (:215).  With the four keep masks passed in, the numbers must match the
+    oracle's training-mode restatement; with masks from torch's generator the call is reproducible under manual_seed and
+    about half of the fc6 activations are dropped."""
+    args = synth.VrdArgs(vrd_in_channels=64, vrd_hidden=512)
+    params = synth.vrd_params(98, args)
+    prd = synth.prd_vectors(5, args.num_relations)
+    fmap = synth.feature_map(33, 1, 64)
+    boxes, rel, masks, classes, ixs, ixo = frame_inputs(orc, 34, 10)
+    n, p, h = len(boxes), len(ixs), 512
+    rng = np.random.default_rng(1)
+    keep = [(rng.random((r, h)) >= 0.5).astype(np.uint8) for r in (n, n, p, p)]
+    net = build(args, params, prd).train()
+    scores, feat = net(fmap, boxes, rel, masks, classes, ixs, ixo, dropout_masks=[torch.from_numpy(k).cuda() for k in keep])
+    want_s, want_f = orc.vrd_forward(params, prd, fmap, boxes, rel, masks, ixs, ixo, nthreads=orc.default_threads(),
+                                     dropout_masks=keep)
+    assert float(np.abs(feat - want_f).max()) <= 2e-2 * float(np.abs(want_f).max())
+    got = scores.cpu().numpy()
+    assert float(np.abs(got - want_s).max()) <= 2e-2 and float(np.abs(got).max()) <= 1.0 + 1e-5     # cosines, not probabilities
+    assert float(np.abs(got.sum(1) - 1).min()) > 1e-3
+    # an unordered-pair shortcut is ignored in training mode (every ordered pair has its own mask)
+    from i2vsgg_b200 import sgg
+    s2, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo, dropout_masks=[torch.from_numpy(k).cuda() for k in keep],
+                rel_unique=sgg.unordered_pairs(n))
+    assert torch.equal(s2, scores)
+    torch.manual_seed(7)
+    a, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo)
+    torch.manual_seed(7)
+    b, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo)
+    assert torch.equal(a, b) and not torch.equal(a, scores)
+    net.eval()
+    e, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo)
+    assert float((e.sum(1) - 1).abs().max()) <= 1e-5
+
+
+def test_vrd_tf32_precision(orc):
+    """precision="tf32": fp32 activations and weights through tcgen05 kind::tf32.  Against the unmodified reference module's
+    output at full width (vrd_golden.npz) the scores agree to 1e-3 relative (2e-2 is the bf16 bar), and a weight update
+    after the first call is picked up (version counters invalidate the derived copies)."""
+    gen = _gen()
+    g = np.load(os.path.join(HERE, "golden", "vrd_golden.npz"))
+    args = synth.VrdArgs()
+    params = synth.vrd_params(gen.PARAM_SEED, args)
+    prd = synth.prd_vectors(gen.PRD_SEED, args.num_relations)
+    fmap, boxes, rel, masks, classes, ixs, ixo = gen.inputs()
+    net = build(args, params, prd)
+    scores, feat = net(fmap, boxes, rel, masks, classes, ixs, ixo, precision="tf32")
+    want_s, want_f = g["full_scores"], g["full_feat"]
+    e_f = float(np.abs(feat - want_f).max()) / float(np.abs(want_f).max())
+    e_s = float(np.abs(scores.cpu().numpy() / want_s - 1).max())
+    s16, f16 = net(fmap, boxes, rel, masks, classes, ixs, ixo)
+    b_f = float(np.abs(f16 - want_f).max()) / float(np.abs(want_f).max())
+    b_s = float(np.abs(s16.cpu().numpy() / want_s - 1).max())
+    print(f"vrd vs the executed reference: tf32 feat {e_f:.2e} scores {e_s:.2e}; bf16 feat {b_f:.2e} scores {b_s:.2e}")
+    assert e_s <= 1e-3 and e_f <= 2e-3
+    with torch.no_grad():
+        net.fc_rel.fc.bias.add_(0.25)
+    s2, _ = net(fmap, boxes, rel, masks, classes, ixs, ixo, precision="tf32")
+    assert not torch.equal(s2, scores)
 
 
 def test_clip_runner_groups_frames_without_changing_records(orc):
