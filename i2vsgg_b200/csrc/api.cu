@@ -98,7 +98,20 @@ extern "C" int ROIPoolForwardLaucher(const float* bottom_data, const float spati
         set_error("ROIPoolForwardLaucher: one frame does not fit the int32 arg-max");
         return 0;
     }
-    int rc = i2v_roi_pool_forward(bottom_data, bottom_rois, top_data, argmax_data, max_batch, channels, height, width, num_rois,
+    // the plane-resident kernel loads whole frames, so it needs the real frame count: read it back from the RoI list
+    int frames = max_batch;
+    if (num_rois > 0 && pooled_height == 7 && pooled_width == 7 && channels % 16 == 0) {
+        size_t have = 0;
+        int* scratch = static_cast<int*>(legacy_scratch(256, &have, stream));
+        int found = 0;
+        if (!scratch || legacy_frame_count(bottom_rois, num_rois, scratch, stream, &found) != I2V_OK) return 0;
+        if (found > max_batch) {
+            set_error("ROIPoolForwardLaucher: frame index %d does not fit the int32 arg-max", found - 1);
+            return 0;
+        }
+        frames = found > 0 ? found : 1;
+    }   // other shapes stay on the per-element kernels, which never touch a frame no RoI names
+    int rc = i2v_roi_pool_forward(bottom_data, bottom_rois, top_data, argmax_data, frames, channels, height, width, num_rois,
                               pooled_height, pooled_width, spatial_scale, I2V_ARGMAX_FLAT, stream);
     return rc == I2V_OK ? 1 : 0;
 }

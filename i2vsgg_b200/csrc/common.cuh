@@ -15,6 +15,11 @@ void set_error(const char* fmt, ...);
 // argument.  Returns nullptr (and sets the error) when the allocation fails; *have receives the buffer size.
 void* legacy_scratch(size_t bytes, size_t* have, cudaStream_t stream);
 
+// For the reference-signature forward launchers, whose argument lists lack the batch size: the largest frame index of
+// the RoI list + 1, found on the device and read back (one 4-byte copy and one synchronisation of `stream`).  *frames = 0
+// when no RoI has a non-negative index.  `scratch` is at least 4 bytes of device memory owned by the caller.
+int legacy_frame_count(const float* rois, int num_rois, int* scratch, cudaStream_t stream, int* frames);
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -1063,6 +1063,19 @@ __global__ void max_frame_kernel(const float* __restrict__ rois, int num_rois, i
 }
 constexpr int kLegacyMaxFrames = 4096;   // beyond this the launcher keeps to the gather kernel (no per-frame lists)
 
+int i2v::legacy_frame_count(const float* rois, int num_rois, int* scratch, cudaStream_t stream, int* frames) {
+    *frames = 0;
+    if (num_rois <= 0) return I2V_OK;
+    int h_max = -1;
+    I2V_CUDA_TRY(cudaMemsetAsync(scratch, 0xff, sizeof(int), stream));
+    max_frame_kernel<<<grid_for(num_rois, 256, 1), 256, 0, stream>>>(rois, num_rois, scratch);
+    I2V_TRY(check_launch("max_frame_kernel"));
+    I2V_CUDA_TRY(cudaMemcpyAsync(&h_max, scratch, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    I2V_CUDA_TRY(cudaStreamSynchronize(stream));
+    *frames = h_max + 1;
+    return I2V_OK;
+}
+
 extern "C" int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
                                       const int height, const int width, const int channels, const int aligned_height,
                                       const int aligned_width, const float* bottom_rois, float* top_data,
@@ -1074,18 +1087,10 @@ extern "C" int ROIAlignForwardLaucher(const float* bottom_data, const float spat
     if (!ws) return 0;
     int frames = INT32_MAX;     // roi_align_kernel.h:13-17: every non-negative frame index is accepted
     if (num_rois > 0 && aligned_height == 7 && aligned_width == 7 && channels % 16 == 0) {
-        int* d_max = reinterpret_cast<int*>(ws);
-        int h_max = -1;
-        if (cudaMemsetAsync(d_max, 0xff, sizeof(int), stream) != cudaSuccess) return 0;
-        max_frame_kernel<<<grid_for(num_rois, 256, 1), 256, 0, stream>>>(bottom_rois, num_rois, d_max);
-        if (cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-            cudaStreamSynchronize(stream) != cudaSuccess) {
-            set_error("ROIAlignForwardLaucher: reading the frame count back failed");
-            cudaGetLastError();
-            return 0;
-        }
-        if (h_max >= 0 && h_max < kLegacyMaxFrames) {
-            frames = h_max + 1;
+        int found = 0;
+        if (legacy_frame_count(bottom_rois, num_rois, reinterpret_cast<int*>(ws), stream, &found) != I2V_OK) return 0;
+        if (found >= 1 && found <= kLegacyMaxFrames) {
+            frames = found;
             const size_t need = i2v_roi_align_workspace_bytes(frames, num_rois);
             ws = static_cast<char*>(legacy_scratch(need + 256, &have, stream));
             if (!ws) return 0;

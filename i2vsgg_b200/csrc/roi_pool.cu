@@ -12,6 +12,7 @@
 // tests as roi_pooling_kernel.cu:160-183 so degenerate RoIs drop out exactly as they do there.
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -286,6 +287,14 @@ int roi_pool_rows_plane(const float* features, const float* rois, void* out, int
                         int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale, long long ldo,
                         int out_dtype, cudaStream_t stream);  // roi_pool_plane.cu
 
+// roi_pool_argmax.cu: plane-resident forward with arg-max, owner-warp backward (no atomics)
+int roi_pool_argmax_forward_plane(const float* features, const float* rois, float* out, int* argmax, int batch, int channels,
+                                  int height, int width, int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                                  int argmax_mode, cudaStream_t stream);
+int roi_pool_backward_owner(const float* grad_out, const float* rois, const int* argmax, float* grad_in, int batch,
+                            int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                            float spatial_scale, int argmax_mode, cudaStream_t stream);
+
 static int pool_args_ok(const char* who, const void* a, const void* b, const void* c, int batch, int channels,
                         int height, int width, int num_rois, int ph, int pw) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0 && height >= 1 && width >= 1 && ph >= 1 && pw >= 1,
@@ -307,6 +316,12 @@ extern "C" int i2v_roi_pool_forward(const float* features, const float* rois, fl
                 "roi_pool_forward: flat arg-max does not fit int32 for this feature tensor");
     int64_t total = (int64_t)num_rois * channels * pooled_h * pooled_w;
     if (total == 0) return I2V_OK;
+    static const bool per_element = getenv("I2V_POOL_PER_ELEMENT") != nullptr;     // tests compare the two paths
+    if (!per_element) {
+        int rc = roi_pool_argmax_forward_plane(features, rois, out, argmax, batch, channels, height, width, num_rois, pooled_h,
+                                               pooled_w, spatial_scale, argmax_mode, stream);
+        if (rc != I2V_ERR_UNSUPPORTED) return rc;
+    }
     int grid = grid_for(total, 256);
     if (argmax_mode == I2V_ARGMAX_FLAT)
         roi_pool_fwd_kernel<I2V_ARGMAX_FLAT><<<grid, 256, 0, stream>>>(features, rois, out, argmax, total, batch, channels, height, width, pooled_h, pooled_w, spatial_scale);
@@ -342,6 +357,13 @@ extern "C" int i2v_roi_pool_backward(const float* grad_out, const float* rois, c
     size_t in_elems = (size_t)batch * channels * height * width;
     if (in_elems == 0) return I2V_OK;
     I2V_REQUIRE(grad_in, "roi_pool_backward: null grad_in");
+    static const bool per_element = getenv("I2V_POOL_PER_ELEMENT") != nullptr;
+    if (!per_element && num_rois > 0) {
+        // owner warps: every gradient plane is accumulated in shared memory by one warp and written once
+        int rc = roi_pool_backward_owner(grad_out, rois, argmax, grad_in, batch, channels, height, width, num_rois, pooled_h,
+                                         pooled_w, spatial_scale, argmax_mode, stream);
+        if (rc != I2V_ERR_UNSUPPORTED) return rc;
+    }
     I2V_CUDA_TRY(cudaMemsetAsync(grad_in, 0, in_elems * sizeof(float), stream));
     int64_t total = (int64_t)num_rois * channels * pooled_h * pooled_w;
     if (total == 0) return I2V_OK;

@@ -534,3 +534,38 @@ def test_roi_align_kernels_agree_on_random_shapes(ops):
                     continue
                 assert float((fout - fref).abs().max()) <= 1e-5 * max(float(fref.abs().max()), 1e-6), (trial, H, W, pool, fimpl)
     assert checked >= 100
+
+
+@pytest.mark.parametrize("mode", ["flat", "plane"])
+@pytest.mark.parametrize("shape", [(2, 32, 38, 63, 90), (1, 16, 63, 38, 40), (3, 48, 20, 31, 60)])
+def test_roi_pool_plane_resident_kernels_equal_the_per_element_ones(ops, orc, mode, shape):
+    """The plane-resident forward (values + arg-max as two TMA stores) and the owner-warp backward (no atomics) against
+    the oracle: values and arg-max bit for bit -- ties (duplicated feature
+    values), RoIs over the border, tiny RoIs (bins under one cell: the bin-by-bin path of the backward), stray frame
+    indices -- and the backward bit-reproducible."""
+    from i2vsgg_b200._lib import ARGMAX_FLAT, ARGMAX_PLANE
+    B, C, H, W, N = shape
+    m = ARGMAX_FLAT if mode == "flat" else ARGMAX_PLANE
+    rng = np.random.default_rng(H + N)
+    feat = np.round(rng.standard_normal((B, C, H, W)) * 2).astype(np.float32) / 2       # many exact ties
+    iw, ih = W * 16.0, H * 16.0
+    x1 = rng.uniform(-40, iw - 10, N); y1 = rng.uniform(-40, ih - 10, N)
+    w = rng.choice([3.0, 30.0, 90.0, 250.0, 600.0], N); h = rng.choice([3.0, 30.0, 90.0, 250.0, 600.0], N)
+    rois = np.stack([rng.integers(0, B, N), x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+    rois[4, 0] = B + 2
+    g = rng.standard_normal((N, C, 7, 7)).astype(np.float32)
+    f, r, go = cuda(feat), cuda(rois), cuda(g)
+    out, arg = ops.roi_pool_forward(f, r, 7, 7, SCALE, m)
+    gin = ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m)
+    ok = rois[:, 0] < B
+    if mode == "flat":
+        wo, wa = orc.roi_pool_forward(feat, rois[ok], 7, 7, SCALE)
+        wg = orc.roi_pool_backward(g[ok], rois[ok], wa, feat.shape, 7, 7, SCALE)
+    else:
+        wo, wa = orc.c_roi_pool_forward(feat, rois[ok], 7, 7, SCALE)
+        wg = orc.c_roi_pool_backward(g[ok], rois[ok], wa, feat.shape, 7, 7)
+    okd = torch.from_numpy(ok).cuda()
+    assert np.array_equal(out[okd].cpu().numpy(), wo) and np.array_equal(arg[okd].cpu().numpy(), wa)
+    assert float(out[~okd].abs().max()) == 0.0 and int(arg[~okd].max()) == -1
+    close(gin, wg)
+    assert torch.equal(gin, ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m))
