@@ -242,6 +242,47 @@ def run_ours(args):
         barrier()
     e2e_ms = reduce_max(start2.elapsed_time(end2))
 
+    # ---- the host<->device ceiling of this box under the same load: every rank copies 512 MiB each way at the same time
+    # (pinned buffers, both copy engines); the end-to-end step cannot beat max(bytes in, bytes out) / this rate
+    ceiling = None
+    if e_steps:
+        nb = 512 << 20
+        hp_in, hp_out = torch.empty(nb, dtype=torch.uint8).pin_memory(), torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dv_in, dv_out = torch.empty(nb, dtype=torch.uint8, device=dev), torch.empty(nb, dtype=torch.uint8, device=dev)
+        c1, c2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def duplex(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            c1.wait_stream(torch.cuda.current_stream())
+            c2.wait_stream(torch.cuda.current_stream())
+            for _ in range(reps):
+                with torch.cuda.stream(c1):
+                    dv_in.copy_(hp_in, non_blocking=True)
+                with torch.cuda.stream(c2):
+                    hp_out.copy_(dv_out, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(c1)
+            torch.cuda.current_stream().wait_stream(c2)
+            b.record()
+            torch.cuda.synchronize()
+            return nb * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+        duplex(1)
+        barrier()
+        mine = duplex(4)
+        if world > 1:
+            t = torch.tensor([mine, -mine, mine], device=dev, dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            lo_rank, agg = -float(tmax[1].item()), float(t[2].item())
+        else:
+            lo_rank, agg = mine, mine
+        need = max(pipe.h2d_bytes, pipe.d2h_bytes)
+        ceiling = {"gbs_each_direction_slowest_rank": lo_rank, "gbs_each_direction_all_ranks": agg,
+                   "frames_per_s_at_ceiling": FRAMES * world / (need / (lo_rank * 1e9)),
+                   "how": "pinned host <-> device, 512 MiB each way at once on two streams, all ranks at the same time"}
+        del hp_in, hp_out, dv_in, dv_out
+
     # ---- parity of the very buffers that were timed (outside the timed regions): the proposals of frames 0 and 17
     # against the oracle's proposal layer, three of their pooled rows against the oracle's RoIAlignAvg
     parity = None
@@ -283,7 +324,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "e2e": {"value": FRAMES * world * e_steps / (e2e_ms * 1e-3) if e_steps else None, "unit": "frames/s", "steps": e_steps,
                     "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
-                    "ms_per_step": e2e_ms / max(e_steps, 1)},
+                    "ms_per_step": e2e_ms / max(e_steps, 1), "ceiling": ceiling},
             "gpu_launches": launches,
             "stages_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -386,6 +427,32 @@ def other_configs(dev, rank: int, world: int, clip_frames_per_rank: int):
                                          "unit": "GB/s", "frac": nbytes / (ms4 * 1e-3) / 1e9 / hbm_peak,
                                          "algorithmic_bytes": nbytes}}
         del grad
+        # ---- the module-API ops the SGG model constructs: ROIPool((7,7), 1/16) forward + backward
+        # (resnet_SGG_emb.py:82) and the model._C RoIAlign (faster_rcnn_SGG_emb.py:47), 8 frames x 300 RoIs
+        from i2vsgg_b200._lib import ARGMAX_PLANE
+        Bm, Nm = 8, 2400
+        featm = torch.randn((Bm, CHANNELS, FEAT_H, FEAT_W), device=dev)
+        roism = torch.from_numpy(synth.rois(402, Nm, batch=Bm, sort_by_batch=True)).to(dev)
+        gradm = torch.randn((Nm, CHANNELS, POOLED, POOLED), device=dev)
+        _, argm = ops.roi_pool_forward(featm, roism, POOLED, POOLED, SCALE, ARGMAX_PLANE)
+        fbytes, pbytes = featm.numel() * 4, gradm.numel() * 4
+
+        def entry(ms, nbytes):
+            return {"ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                    "unit": "GB/s", "algorithmic_bytes": nbytes}
+        out["module_ops"] = {
+            "workload": "8 frames x 300 RoIs, 1024 x 38 x 63, 7x7 (fractions of the measured HBM copy bandwidth)",
+            "roi_pool_fwd": entry(timed(lambda: ops.roi_pool_forward(featm, roism, POOLED, POOLED, SCALE, ARGMAX_PLANE), reps=10),
+                                  fbytes + 2 * pbytes),
+            "roi_pool_bwd": entry(timed(lambda: ops.roi_pool_backward(gradm, roism, argm, featm.shape, POOLED, POOLED, SCALE,
+                                                                      ARGMAX_PLANE), reps=10), fbytes + 2 * pbytes),
+            "c_roi_align_fwd": entry(timed(lambda: ops.c_roi_align_forward(featm, roism, POOLED, POOLED, SCALE, 0), reps=10),
+                                     fbytes + pbytes),
+            "c_roi_align_bwd": entry(timed(lambda: ops.c_roi_align_backward(gradm, roism, featm.shape, POOLED, POOLED, SCALE, 0),
+                                           reps=10), fbytes + pbytes),
+            "note": "model._C has no source in the reference tree: parity of these two ops is pinned to torchvision only",
+        }
+        del featm, gradm, argm
 
     # ---- configs[4]
     frames = clip_frames_per_rank * world

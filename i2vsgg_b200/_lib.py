@@ -40,6 +40,8 @@ SIGNATURES = {
     "i2v_nms_dets": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "i2v_proposal_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "i2v_proposal_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_proposal_forward_chunk": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "i2v_rois_add_frame": (_i, [_vp, _i, _i, _vp]),
     "i2v_proposal_forward_scores": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "i2v_rpn_cls_prob": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "i2v_proposal_stages": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -270,6 +270,7 @@ struct NmsArgs {
     float* spill_area;       // [sets][n]
     float* out_rois;         // optional [sets][post][5]
     int post;
+    int frame_base;          // column 0 of out_rois = frame_base + set (a chunk of a larger batch keeps the batch's numbering)
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs a) {
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
         for (int k = tid; k < a.post; k += kNmsThreads) {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < nk) bx = (k < kNmsKeptSmem) ? kbox[k] : sp_box[k];
-            o[k * 5 + 0] = (float)set;
+            o[k * 5 + 0] = (float)(a.frame_base + set);
             o[k * 5 + 1] = bx.x;
             o[k * 5 + 2] = bx.y;
             o[k * 5 + 3] = bx.z;
@@ -562,7 +563,7 @@ static int proposal_forward_impl(bool from_scores, const float* cls_prob, const 
                                  const float* base_anchors, int batch, int num_anchors, int height, int width,
                                  int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
                                  float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int frame_base = 0) {
     NmsWs w;
     int ka;
     I2V_TRY(proposal_common(cls_prob, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width, feat_stride,
@@ -595,6 +596,7 @@ static int proposal_forward_impl(bool from_scores, const float* cls_prob, const 
     a.spill_area = w.spill_area;
     a.out_rois = out_rois;
     a.post = post_nms_top_n;
+    a.frame_base = frame_base;
     // the spill arrays are indexed by kept slot < a.n <= ka: carved for ka per frame
     a.spill_box = w.spill_box;
     return launch_nms(a, batch, stream);
@@ -608,6 +610,32 @@ extern "C" int i2v_proposal_forward(const float* cls_prob, const float* bbox_pre
     return proposal_forward_impl(false, cls_prob, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width,
                                  feat_stride, pre_nms_top_n, post_nms_top_n, nms_thresh, out_rois, out_counts, workspace,
                                  workspace_bytes, stream);
+}
+
+// A chunk of a larger batch: the frames are numbered frame_base, frame_base + 1, ... in column 0 of out_rois
+// (proposal_layer.py:160 writes the index inside the batch the layer was called with).
+extern "C" int i2v_proposal_forward_chunk(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                          const float* base_anchors, int batch, int num_anchors, int height, int width,
+                                          int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
+                                          int frame_base, float* out_rois, int* out_counts, void* workspace,
+                                          size_t workspace_bytes, cudaStream_t stream) {
+    return proposal_forward_impl(false, cls_prob, bbox_pred, im_info, base_anchors, batch, num_anchors, height, width,
+                                 feat_stride, pre_nms_top_n, post_nms_top_n, nms_thresh, out_rois, out_counts, workspace,
+                                 workspace_bytes, stream, frame_base);
+}
+
+// rois[n, 0] += offset: a chunk that was processed with chunk-local frame numbers (what the RoI kernels of the chunk need)
+// gets the numbering of the whole batch back before it leaves the device.
+__global__ void rois_add_frame_kernel(float* __restrict__ rois, int num_rois, float offset) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < num_rois) rois[(size_t)n * 5] += offset;
+}
+extern "C" int i2v_rois_add_frame(float* rois, int num_rois, int offset, cudaStream_t stream) {
+    I2V_REQUIRE(num_rois >= 0, "rois_add_frame: bad size");
+    if (num_rois == 0 || offset == 0) return I2V_OK;
+    I2V_REQUIRE(rois, "rois_add_frame: null pointer");
+    rois_add_frame_kernel<<<ceil_div(num_rois, 256), 256, 0, stream>>>(rois, num_rois, (float)offset);
+    return check_launch("rois_add_frame_kernel");
 }
 
 // rpn.py:63-78: the same layer fed with the RPN head's raw class scores; the 2-way softmax and the foreground slice are

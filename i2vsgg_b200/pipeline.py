@@ -177,8 +177,9 @@ class HostPipeline:
             main.wait_event(ready)
             self._run(d["cls"][f0:f1], d["reg"][f0:f1], d["info"][f0:f1], d["feat"][f0:f1], d["grad"][r0:r1],
                       self.rois[f0:f1], self.pooled[r0:r1], self.grad_in[f0:f1], f1 - f0)
-            if f0:
-                self.rois[f0:f1, :, 0] += float(f0)      # frame indices of the whole batch, as device_step writes them
+            if f0:      # frame indices of the whole batch, as device_step writes them
+                check(self.lib.i2v_rois_add_frame(_p(self.rois[f0:f1]), (f1 - f0) * post, f0,
+                                                  ctypes.c_void_p(main.cuda_stream)), "rois_add_frame")
             done = main.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)

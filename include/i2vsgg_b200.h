@@ -166,6 +166,14 @@ int i2v_proposal_forward(const float* cls_prob, const float* bbox_pred, const fl
                          int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh,
                          float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
+/* The same for a chunk of a larger batch: column 0 of out_rois counts from frame_base. */
+int i2v_proposal_forward_chunk(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                               const float* base_anchors, int batch, int num_anchors, int height, int width,
+                               int feat_stride, int pre_nms_top_n, int post_nms_top_n, float nms_thresh, int frame_base,
+                               float* out_rois, int* out_counts, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream);
+/* rois [N,5]: column 0 += offset (a chunk processed with chunk-local frame numbers gets the batch's numbering back). */
+int i2v_rois_add_frame(float* rois, int num_rois, int offset, cudaStream_t stream);
 /* The step before the layer (rpn.py:63-78): rpn_cls_score [B,2A,H,W] -> rpn_cls_prob [B,2A,H,W], the softmax over each
  * anchor's (background, foreground) pair of channels (a, a+A). */
 int i2v_rpn_cls_prob(const float* cls_score, float* cls_prob, int batch, int num_anchors, int height, int width,
