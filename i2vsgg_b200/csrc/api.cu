@@ -4,6 +4,7 @@
 // device buffer per (thread, device, stream); everything else in the library takes the caller's workspace.
 #include <limits.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <utility>
@@ -100,7 +101,7 @@ extern "C" int ROIPoolForwardLaucher(const float* bottom_data, const float spati
     }
     // the plane-resident kernel loads whole frames, so it needs the real frame count: read it back from the RoI list
     int frames = max_batch;
-    if (num_rois > 0 && pooled_height == 7 && pooled_width == 7 && channels % 16 == 0) {
+    if (getenv("I2V_POOL_PLANE") != nullptr && num_rois > 0 && pooled_height == 7 && pooled_width == 7 && channels % 16 == 0) {
         size_t have = 0;
         int* scratch = static_cast<int*>(legacy_scratch(256, &have, stream));
         int found = 0;

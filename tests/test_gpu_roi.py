@@ -539,10 +539,11 @@ def test_roi_align_kernels_agree_on_random_shapes(ops):
 @pytest.mark.parametrize("mode", ["flat", "plane"])
 @pytest.mark.parametrize("shape", [(2, 32, 38, 63, 90), (1, 16, 63, 38, 40), (3, 48, 20, 31, 60)])
 def test_roi_pool_plane_resident_kernels_equal_the_per_element_ones(ops, orc, mode, shape):
-    """The plane-resident forward (values + arg-max as two TMA stores) and the owner-warp backward (no atomics) against
-    the oracle: values and arg-max bit for bit -- ties (duplicated feature
+    """The opt-in plane-resident forward (values + arg-max as two TMA stores) and owner-warp backward (no atomics; both
+    I2V_POOL_PLANE=1) against the default per-element kernels and the oracle: values and arg-max bit for bit -- ties (duplicated feature
     values), RoIs over the border, tiny RoIs (bins under one cell: the bin-by-bin path of the backward), stray frame
     indices -- and the backward bit-reproducible."""
+    import os
     from i2vsgg_b200._lib import ARGMAX_FLAT, ARGMAX_PLANE
     B, C, H, W, N = shape
     m = ARGMAX_FLAT if mode == "flat" else ARGMAX_PLANE
@@ -555,8 +556,17 @@ def test_roi_pool_plane_resident_kernels_equal_the_per_element_ones(ops, orc, mo
     rois[4, 0] = B + 2
     g = rng.standard_normal((N, C, 7, 7)).astype(np.float32)
     f, r, go = cuda(feat), cuda(rois), cuda(g)
-    out, arg = ops.roi_pool_forward(f, r, 7, 7, SCALE, m)
-    gin = ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m)
+    ref_out, ref_arg = ops.roi_pool_forward(f, r, 7, 7, SCALE, m)              # the default per-element kernels
+    ref_gin = ops.roi_pool_backward(go, r, ref_arg, feat.shape, 7, 7, SCALE, m)
+    os.environ["I2V_POOL_PLANE"] = "1"                                          # read per call
+    try:
+        out, arg = ops.roi_pool_forward(f, r, 7, 7, SCALE, m)
+        gin = ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m)
+        again = ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m)
+    finally:
+        del os.environ["I2V_POOL_PLANE"]
+    assert torch.equal(out, ref_out) and torch.equal(arg, ref_arg) and torch.equal(gin, again)
+    assert float((gin - ref_gin).abs().max()) <= 1e-5 * float(ref_gin.abs().max())
     ok = rois[:, 0] < B
     if mode == "flat":
         wo, wa = orc.roi_pool_forward(feat, rois[ok], 7, 7, SCALE)
@@ -568,4 +578,3 @@ def test_roi_pool_plane_resident_kernels_equal_the_per_element_ones(ops, orc, mo
     assert np.array_equal(out[okd].cpu().numpy(), wo) and np.array_equal(arg[okd].cpu().numpy(), wa)
     assert float(out[~okd].abs().max()) == 0.0 and int(arg[~okd].max()) == -1
     close(gin, wg)
-    assert torch.equal(gin, ops.roi_pool_backward(go, r, arg, feat.shape, 7, 7, SCALE, m))
