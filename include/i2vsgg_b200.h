@@ -85,6 +85,9 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
 #define I2V_IMPL_SLAB 6    /* forward only: the 16 planes of a CTA arrive as one TMA bulk copy and are used in place as
                               [channel][row][col] (what AUTO picks for 38x63 / 63x38 maps); I2V_ERR_UNSUPPORTED elsewhere
                               and in the backward                                                                          */
+#define I2V_IMPL_EVEN 7    /* forward only: the planes re-pitched in place to an even row pitch, so that the two half-warps
+                              of a load are on opposite bank parities by construction (W <= 64, H <= 40; measured 7 %
+                              slower than I2V_IMPL_SLAB on config 2); I2V_ERR_UNSUPPORTED elsewhere and in the backward      */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.

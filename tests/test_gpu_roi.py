@@ -43,10 +43,12 @@ CASES = [  # (batch, channels, H, W, num_rois)
 
 
 @pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane"])
+@pytest.mark.parametrize("impl", ["gather", "plane", "slab", "even", "auto"])
 @pytest.mark.parametrize("case", CASES)
 def test_roi_align_forward(ops, orc, case, impl, pool):
     B, C, H, W, N = case
+    if impl in ("slab", "even") and (pool == "max" or (impl == "slab" and (H * W) % 4 != 2)):
+        pytest.skip("slab / even-pitch kernels: pool none / avg (slab: H * W = 2 mod 4)")
     feat = synth.feature_map(100 + B, B, C, H, W)
     rois = synth.rois(200 + N, N, batch=B)
     if W != 63:
@@ -404,7 +406,7 @@ def test_roi_align_properties_at_config2_size(ops, orc):
     close(out[torch.from_numpy(few).cuda()], want)
 
     # the kernel bench.py times (`auto` -> the slab kernel on a 38x63 map), held to the same bar
-    for impl in ("auto", "slab"):
+    for impl in ("auto", "even", "slab"):
         fast = ops.roi_align_forward(feat, rois, 7, 7, SCALE, "avg", impl)
         assert float((fast[pick] - ref).abs().max()) <= 1e-5 * scale, impl
         close(fast[torch.from_numpy(few).cuda()], want)
@@ -527,7 +529,7 @@ def test_roi_align_kernels_agree_on_random_shapes(ops):
                 assert torch.equal(out, ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, impl))
                 checked += 1
             fref = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, "gather")
-            for fimpl in ("auto", "slab", "plane"):
+            for fimpl in ("auto", "even", "slab", "plane"):
                 try:
                     fout = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, fimpl)
                 except I2VError:
