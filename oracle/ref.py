@@ -287,14 +287,18 @@ def py_bbox_transform_inv_clip(anchors, deltas, im_info):
     return clip_boxes(p, torch.from_numpy(im_info), B).numpy()
 
 
-def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial, classes, ix1, ix2):
+def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial, classes, ix1, ix2, train_masks=None):
     """Executes `vrd.forward` (lib/model/faster_rcnn/resnet_SGG_emb.py:128-221) UNMODIFIED on the CPU.
 
     What is stubbed, and only that: `model._C` has no source in the reference (lib/setup.py:19), so
     `model.roi_layers.ROIPool` is bound to torchvision.ops.roi_pool (the same maskrcnn-benchmark op); the detector base
     class `_fasterRCNN` (not on this path) is an empty nn.Module; `.cuda()` is the identity because the build container
     has no GPU; the three annotation pickles the constructor opens (:75-80) are empty temporaries.
-    `params` maps the reference's state_dict keys to numpy arrays.  Returns (scores [P,n_rel], feat [P,emb])."""
+    `params` maps the reference's state_dict keys to numpy arrays.  Returns (scores [P,n_rel], feat [P,emb]).
+
+    `train_masks` (four keep masks, in the order of the F.dropout calls at :148, :149, :162, :163) runs the module in
+    TRAINING mode with one more stub: the module's `F.dropout` applies those masks (x * keep / (1 - p), p = 0.5) instead of
+    drawing its own, so that the result is reproducible."""
     _py_setup()
     import pickle
     import tempfile
@@ -335,6 +339,21 @@ def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial
         sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()}
         missing = net.load_state_dict(sd, strict=True)
         net.eval()
+        old_f = ref_mod.F
+        if train_masks is not None:
+            net.train()
+            queue = [torch.from_numpy(np.asarray(m, np.float32)) for m in train_masks]
+
+            class _F:
+                def __getattr__(self, name):
+                    return getattr(old_f, name)
+
+                @staticmethod
+                def dropout(x, p=0.5, training=True, inplace=False):
+                    assert training and p == 0.5
+                    return x * queue.pop(0) * 2.0
+
+            ref_mod.F = _F()
         net.obj_vecs = np.zeros((args.num_classes + 1, 300), np.float32)
         with torch.no_grad():
             scores, feat = net(np.asarray(fmap, np.float32), np.asarray(boxes, np.float32),
@@ -342,6 +361,10 @@ def py_vrd_forward(params: dict, args, prd_vecs, fmap, boxes, rel_boxes, spatial
                                list(classes), np.asarray(ix1), np.asarray(ix2))
     finally:
         torch.Tensor.cuda = old_cuda
+        try:
+            ref_mod.F = old_f
+        except NameError:
+            pass
     return scores.numpy(), feat
 
 

@@ -31,6 +31,13 @@ def inputs():
     return fmap, boxes, rel, masks, classes, ixs, ixo
 
 
+def train_masks(hidden: int = 4096):
+    """The four keep masks of the training-mode run (F.dropout calls at resnet_SGG_emb.py:148, :149, :162, :163)."""
+    rng = np.random.default_rng(77)
+    p = NUM_DET * (NUM_DET - 1)
+    return [(rng.random((r, hidden)) >= 0.5).astype(np.uint8) for r in (NUM_DET, NUM_DET, p, p)]
+
+
 def main():
     assert ref.have_py_ref(), "/root/reference is not mounted"
     g = {}
@@ -44,6 +51,12 @@ def main():
         scores, feat = ref.py_vrd_forward(params, args, prd, fmap, boxes, rel, spatial, classes, ixs, ixo)
         g[f"{tag}_scores"], g[f"{tag}_feat"] = scores.astype(np.float32), feat.astype(np.float32)
         print(tag, scores.shape, feat.shape, float(scores.max()), float(np.abs(feat).max()))
+        if tag == "full":
+            # the same module in training mode: dropout with the supplied keep masks, no softmax (:148-151, :215)
+            ts, tf = ref.py_vrd_forward(params, args, prd, fmap, boxes, rel, spatial, classes, ixs, ixo,
+                                        train_masks=train_masks())
+            g["train_scores"], g["train_feat"] = ts.astype(np.float32), tf.astype(np.float32)
+            print("train", ts.shape, float(np.abs(ts).max()), float(np.abs(tf).max()))
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -42,13 +42,22 @@ CASES = [  # (batch, channels, H, W, num_rois)
 ]
 
 
-@pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane", "slab", "even", "auto"])
-@pytest.mark.parametrize("case", CASES)
+def _fwd_combos():
+    # every (case, impl, pool) the kernels take: the slab / even-pitch kernels have no max pool, the slab kernel needs
+    # H * W = 2 (mod 4)
+    for case in CASES:
+        for impl in ("gather", "plane", "slab", "even", "auto"):
+            for pool in ("none", "avg", "max"):
+                if impl in ("slab", "even") and pool == "max":
+                    continue
+                if impl == "slab" and (case[2] * case[3]) % 4 != 2:
+                    continue
+                yield case, impl, pool
+
+
+@pytest.mark.parametrize("case,impl,pool", list(_fwd_combos()))
 def test_roi_align_forward(ops, orc, case, impl, pool):
     B, C, H, W, N = case
-    if impl in ("slab", "even") and (pool == "max" or (impl == "slab" and (H * W) % 4 != 2)):
-        pytest.skip("slab / even-pitch kernels: pool none / avg (slab: H * W = 2 mod 4)")
     feat = synth.feature_map(100 + B, B, C, H, W)
     rois = synth.rois(200 + N, N, batch=B)
     if W != 63:
@@ -96,15 +105,22 @@ def test_roi_align_empty(ops):
     assert float(g.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("pool", ["none", "avg", "max"])
-@pytest.mark.parametrize("impl", ["gather", "plane", "rows", "phase", "band", "auto"])
-@pytest.mark.parametrize("case", CASES + [(2, 64, 38, 63, 80)])
+def _bwd_combos():
+    # the max pool's arg-max routing needs the features: gather kernel (and `auto`, which takes it) only; the band-owner
+    # kernel takes 32 channels per CTA
+    for case in CASES + [(2, 64, 38, 63, 80)]:
+        for impl in ("gather", "plane", "rows", "phase", "band", "auto"):
+            for pool in ("none", "avg", "max"):
+                if impl in ("plane", "rows", "phase", "band") and pool == "max":
+                    continue
+                if impl == "band" and case[1] % 32:
+                    continue
+                yield case, impl, pool
+
+
+@pytest.mark.parametrize("case,impl,pool", list(_bwd_combos()))
 def test_roi_align_backward(ops, orc, case, impl, pool):
-    if impl in ("plane", "rows", "phase", "band") and pool == "max":
-        pytest.skip("the max pool's arg-max routing needs the features: gather kernel only")
     B, C, H, W, N = case
-    if impl == "band" and C % 32:
-        pytest.skip("the band-owner kernel takes 32 channels per CTA")
     feat = synth.feature_map(100 + B, B, C, H, W)
     rois = synth.rois(200 + N, N, batch=B)
     if W != 63:

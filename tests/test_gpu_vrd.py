@@ -234,6 +234,24 @@ def test_vrd_training_mode_dropout_and_raw_scores(orc):
     assert float((e.sum(1) - 1).abs().max()) <= 1e-5
 
 
+def test_vrd_training_mode_against_the_executed_reference(orc):
+    """Full width, training mode: our forward with the golden run's keep masks against the UNMODIFIED reference module
+    executed in training mode (vrd_golden.npz: train_scores / train_feat), in both precisions."""
+    gen = _gen()
+    g = np.load(os.path.join(HERE, "golden", "vrd_golden.npz"))
+    args = synth.VrdArgs()
+    net = build(args, synth.vrd_params(gen.PARAM_SEED, args), synth.prd_vectors(gen.PRD_SEED, args.num_relations)).train()
+    fmap, boxes, rel, masks, classes, ixs, ixo = gen.inputs()
+    keep = [torch.from_numpy(m).cuda() for m in gen.train_masks()]
+    want_s, want_f = g["train_scores"], g["train_feat"]
+    for precision, bar_f, bar_s in (("bf16", 2e-2, 2e-2), ("tf32", 2e-3, 1e-3)):
+        scores, feat = net(fmap, boxes, rel, masks, classes, ixs, ixo, dropout_masks=keep, precision=precision)
+        e_f = float(np.abs(feat - want_f).max()) / float(np.abs(want_f).max())
+        e_s = float(np.abs(scores.cpu().numpy() - want_s).max())           # cosine similarities in [-1, 1]
+        print(f"vrd train vs the executed reference, {precision}: feat {e_f:.2e} scores {e_s:.2e}")
+        assert e_f <= bar_f and e_s <= bar_s
+
+
 def test_vrd_tf32_precision(orc):
     """precision="tf32": fp32 activations and weights through tcgen05 kind::tf32.  Against the unmodified reference module's
     output at full width (vrd_golden.npz) the scores agree to 1e-3 relative (2e-2 is the bf16 bar), and a weight update

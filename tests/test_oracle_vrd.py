@@ -43,3 +43,19 @@ def test_vrd_oracle_matches_the_reference_module(vrd_golden, tag, kw):
                                 args.spatial_type, rows=[5, 0, 11], nthreads=oracle.default_threads())
     np.testing.assert_allclose(f2, feat[[5, 0, 11]], rtol=0, atol=1e-5 * float(np.abs(feat).max()))
     np.testing.assert_allclose(s2, scores[[5, 0, 11]], rtol=1e-5, atol=1e-8)
+
+
+def test_vrd_oracle_training_mode_matches_the_reference_module(vrd_golden):
+    """The reference module executed in TRAINING mode (dropout with the supplied keep masks, raw cosine similarities:
+    resnet_SGG_emb.py:148-151,215) pins the oracle's training-mode restatement."""
+    gen = _gen()
+    args = synth.VrdArgs()
+    params = synth.vrd_params(gen.PARAM_SEED, args)
+    prd = synth.prd_vectors(gen.PRD_SEED, args.num_relations)
+    fmap, boxes, rel, masks, classes, ixs, ixo = gen.inputs()
+    scores, feat = oracle.vrd_forward(params, prd, fmap, boxes, rel, masks, ixs, ixo, nthreads=oracle.default_threads(),
+                                      dropout_masks=gen.train_masks())
+    want_s, want_f = vrd_golden["train_scores"], vrd_golden["train_feat"]
+    np.testing.assert_allclose(feat, want_f, rtol=0, atol=2e-4 * float(np.abs(want_f).max()))
+    np.testing.assert_allclose(scores, want_s, rtol=0, atol=1e-4)
+    assert float(np.abs(want_s).max()) <= 1.0 and abs(float(want_s.sum(1)[0]) - 1.0) > 1e-3      # cosines, not probabilities
