@@ -27,7 +27,7 @@ static_assert(sizeof(SlabTab) == 192 && sizeof(SlabTab) <= kRoiTabSlotBytes, "Sl
 namespace {
 
 constexpr int kK = 16;
-constexpr int kWarps = 10;          // each works on two RoIs at a time (one per half-warp)
+constexpr int kWarps = 11;          // each works on two RoIs at a time (one per half-warp); 11 is what fits beside the planes
 constexpr int kThreads = kWarps * 32;
 constexpr int kTabV = (int)(sizeof(SlabTab) / 16);      // 12 16-byte pieces
 
