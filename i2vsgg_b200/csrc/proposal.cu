@@ -121,10 +121,12 @@ __device__ __forceinline__ unsigned desc_key(float f) {
 __global__ void __launch_bounds__(kSortThreads) segment_sort_kernel(const float* __restrict__ keys, int n,
                                                                     int key_stride, int64_t seg_stride,
                                                                     unsigned* buf_k, unsigned* buf_i,
-                                                                    int* __restrict__ order_out, int64_t order_stride) {
+                                                                    int* __restrict__ order_out, int64_t order_stride,
+                                                                    const int* __restrict__ gate) {
     __shared__ unsigned hist[kSortWarps][256];
     __shared__ unsigned digit_base[256];
     const int seg = blockIdx.x;
+    if (gate && gate[seg] == 0) return;  // the short path already finished this segment
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* kin = keys + (size_t)seg * seg_stride;
     unsigned* k0 = buf_k + (size_t)seg * 2 * n;
@@ -235,6 +237,223 @@ __global__ void __launch_bounds__(kSortThreads) segment_sort_kernel(const float*
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ top-K order
+// NMS with a small post_nms_topN stops after a few thousand candidates (2.2-2.9 K on the bench workload), so ordering all
+// K*A = 21.5 K scores of a frame is mostly wasted.  These CTAs order only the kTopK best, kTopKPart ranks per CTA and with
+// no communication between the CTAs of a frame: CTA c finds, by radix SELECT over the composite (desc_key, index) --
+// unique, so ties need no special case -- the composites of rank c*kTopKPart and (c+1)*kTopKPart (16-bit digits, one
+// counting sweep per digit, the first sweep shared by both ranks), compacts what lies between them into registers, one
+// composite per thread, and orders them with a bitonic network (shuffles below distance 32, shared memory above); the low
+// word of a composite is the row.  The result equals the first kTopK entries of the stable full sort bit for bit.  If NMS
+// runs out of these candidates before it has post_nms_topN boxes it raises the frame's retry flag and the full sort + a
+// second NMS run, gated on that flag, redo the frame (rare; see proposal_forward_impl).
+constexpr int kTopK = 4096;
+constexpr int kTopKPart = 1024;
+constexpr int kTopKThreads = 1024;
+constexpr int kTopKBatch = 8;
+constexpr int kTopKHistWords = 32768;  // 65536 bins of 16 bits, two per word: needs n <= 65535
+constexpr size_t kTopKSmemBytes = (size_t)kTopKHistWords * 4 + (size_t)2 * kTopKPart * 8;
+static_assert(kTopKPart == kTopKThreads, "one composite per thread");
+
+__global__ void __launch_bounds__(kTopKThreads, 1) segment_topk_kernel(const float* __restrict__ keys, int n, int key_stride,
+                                                                       int64_t seg_stride, int* __restrict__ order_out,
+                                                                       int64_t order_stride, int need) {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    unsigned* hist = reinterpret_cast<unsigned*>(tk_smem);
+    unsigned long long* xch = reinterpret_cast<unsigned long long*>(tk_smem + (size_t)kTopKHistWords * 4);   // [2][kTopKPart]
+    __shared__ unsigned s_wtot[32];
+    __shared__ unsigned s_owner, s_excl, s_digit, s_krem, s_binc, s_cnt;
+
+    const int seg = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank_lo = (int)blockIdx.x * kTopKPart;               // this CTA orders ranks (rank_lo, rank_hi], 1-based
+    const int rank_hi = min(min(n, need), rank_lo + kTopKPart);
+    if (rank_hi <= rank_lo) return;
+    const float* kin = keys + (size_t)seg * seg_stride;
+    int* out = order_out + (size_t)seg * order_stride;
+
+    // one counting sweep: histogram of a 16-bit digit over the keys that match the digits fixed so far
+    auto sweep = [&](int pass, unsigned p0, unsigned p1) {
+        for (int i = tid; i < kTopKHistWords / 4; i += kTopKThreads) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        // eight loads in flight per thread: the sweep pays the L2 latency once per 8 K keys, not once per 1 K
+        for (int base = tid; base < n; base += kTopKBatch * kTopKThreads) {
+            unsigned kv[kTopKBatch];
+#pragma unroll
+            for (int q = 0; q < kTopKBatch; ++q) {
+                const int i = base + q * kTopKThreads;
+                kv[q] = i < n ? desc_key(kin[(size_t)i * key_stride]) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < kTopKBatch; ++q) {
+                const int i = base + q * kTopKThreads;
+                const unsigned kk = kv[q];
+                unsigned d;
+                bool match;
+                if (pass == 0) {
+                    d = kk >> 16;
+                    match = true;
+                } else if (pass == 1) {
+                    d = kk & 0xffffu;
+                    match = (kk >> 16) == p0;
+                } else {
+                    d = (unsigned)i;        // n <= 65535: the index is one digit
+                    match = kk == ((p0 << 16) | p1);
+                }
+                if (match && i < n) atomicAdd(&hist[d >> 1], (d & 1u) ? 65536u : 1u);
+            }
+        }
+        __syncthreads();
+    };
+    // which bin of the current histogram holds its krem-th entry (1-based): digit, rank inside the bin, size of the bin.
+    // Thread t owns bins [64t, 64t + 64) (words rotated by t: no bank conflicts).
+    auto locate = [&](unsigned krem, unsigned& digit, unsigned& krem_in, unsigned& binc) {
+        unsigned sum = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) {
+            const unsigned v = hist[32 * tid + ((w + tid) & 31)];
+            sum += (v & 0xffffu) + (v >> 16);
+        }
+        unsigned incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        unsigned before = 0;
+        for (int w = 0; w < warp; ++w) before += s_wtot[w];
+        const unsigned excl = before + incl - sum;
+        if (excl < krem && krem <= excl + sum) {
+            s_owner = (unsigned)tid;
+            s_excl = excl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned word = 32u * s_owner + (unsigned)lane;
+            const unsigned v = hist[word], c0 = v & 0xffffu, c1 = v >> 16, sw = c0 + c1;
+            unsigned in2 = sw;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, in2, o);
+                if (lane >= o) in2 += t;
+            }
+            const unsigned e = s_excl + in2 - sw;
+            if (e < krem && krem <= e + sw) {
+                const unsigned r = krem - e;
+                if (r <= c0) {
+                    s_digit = 2u * word;
+                    s_krem = r;
+                    s_binc = c0;
+                } else {
+                    s_digit = 2u * word + 1u;
+                    s_krem = r - c0;
+                    s_binc = c1;
+                }
+            }
+        }
+        __syncthreads();
+        digit = s_digit;
+        krem_in = s_krem;
+        binc = s_binc;
+        __syncthreads();                                           // s_* are rewritten by the next call
+    };
+
+    // the composites of rank rank_hi and rank_lo; a bin that is wanted whole ends the descent (bound = its upper edge)
+    unsigned long long t_hi = ~0ull, t_lo = 0ull;
+    const bool want_hi = rank_hi < n, want_lo = rank_lo > 0;       // otherwise: everything up to the end / from the start
+    if (want_hi || want_lo) {
+        sweep(0, 0, 0);
+        unsigned dh = 0, kh = 0, bh = 0, dl = 0, kl = 0, bl = 0;
+        if (want_hi) locate((unsigned)rank_hi, dh, kh, bh);
+        if (want_lo) locate((unsigned)rank_lo, dl, kl, bl);
+        unsigned long long* bound[2] = {&t_hi, &t_lo};
+        const bool want[2] = {want_hi, want_lo};
+        const unsigned d0[2] = {dh, dl}, k0[2] = {kh, kl}, b0[2] = {bh, bl};
+        unsigned swept_p0 = 0xffffffffu;                           // the pass-1 histogram in shared memory belongs to this digit
+        for (int w = 0; w < 2; ++w) {
+            if (!want[w]) continue;
+            const unsigned p0 = d0[w];
+            unsigned krem = k0[w];
+            *bound[w] = ((unsigned long long)p0 << 48) | 0xffffffffffffull;
+            if (b0[w] == krem) continue;
+            if (swept_p0 != p0) sweep(1, p0, 0);
+            swept_p0 = p0;
+            unsigned p1, binc;
+            locate(krem, p1, krem, binc);
+            *bound[w] = ((unsigned long long)((p0 << 16) | p1) << 32) | 0xffffffffull;
+            if (binc == krem) continue;
+            sweep(2, p0, p1);
+            swept_p0 = 0xffffffffu;
+            unsigned di;
+            locate(krem, di, krem, binc);
+            *bound[w] = ((unsigned long long)((p0 << 16) | p1) << 32) | (unsigned long long)di;
+        }
+    }
+
+    // compaction into shared memory (unordered: the network orders them, and they are unique)
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kTopKBatch * kTopKThreads) {
+        unsigned kv[kTopKBatch];
+#pragma unroll
+        for (int q = 0; q < kTopKBatch; ++q) {
+            const int i = base + q * kTopKThreads + tid;
+            kv[q] = i < n ? desc_key(kin[(size_t)i * key_stride]) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < kTopKBatch; ++q) {
+            const int i = base + q * kTopKThreads + tid;
+            const unsigned long long c = ((unsigned long long)kv[q] << 32) | (unsigned)i;
+            const bool sel = i < n && c <= t_hi && (!want_lo || c > t_lo);
+            const unsigned m = __ballot_sync(0xffffffffu, sel);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned b = 0;
+                if (lane == leader) b = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (sel) xch[b + __popc(m & ((1u << lane) - 1u))] = c;
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = (int)s_cnt;                                    // rank_hi - rank_lo
+    unsigned long long v = tid < cnt ? xch[tid] : ~0ull;
+    __syncthreads();
+
+    // bitonic network over the CTA's registers, ascending: thread t ends up with the composite of rank rank_lo + t + 1
+    int buf = 0;
+    for (int k = 2; k <= kTopKPart; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long o;
+            if (j < 32) {
+                o = __shfl_xor_sync(0xffffffffu, v, j);
+            } else {
+                unsigned long long* x = xch + buf * kTopKPart;
+                x[tid] = v;
+                __syncthreads();
+                o = x[tid ^ j];
+                buf ^= 1;                                          // the next exchange writes the other buffer: one barrier each
+            }
+            const bool keep_min = ((tid & j) == 0) == ((tid & k) == 0);
+            if ((o < v) == keep_min) v = o;
+        }
+    }
+    if (tid < cnt) out[rank_lo + tid] = (int)(unsigned)(v & 0xffffffffull);
+}
+
+static bool topk_order_ok(int n) { return n >= 1 && n <= 65535; }
+
+// orders the min(n, need, kTopK) best keys of every segment
+static int launch_topk_order(const float* keys, int segments, int n, int key_stride, int64_t seg_stride, int* order,
+                             int64_t order_stride, int need, cudaStream_t stream) {
+    I2V_CUDA_TRY(cudaFuncSetAttribute(segment_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopKSmemBytes));
+    const int want = min(min(n, need), kTopK);
+    dim3 grid(ceil_div(want, kTopKPart), segments);
+    segment_topk_kernel<<<grid, kTopKThreads, kTopKSmemBytes, stream>>>(keys, n, key_stride, seg_stride, order, order_stride, want);
+    return check_launch("segment_topk_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ NMS
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
@@ -271,6 +490,9 @@ struct NmsArgs {
     float* out_rois;         // optional [sets][post][5]
     int post;
     int frame_base;          // column 0 of out_rois = frame_base + set (a chunk of a larger batch keeps the batch's numbering)
+    const int* gate;         // optional [sets]: a set whose entry is 0 is skipped (its result is already final)
+    int* retry;              // optional [sets]: set to 1 when the candidates ran out before max_keep boxes were kept and
+    int more;                //   `more` says that the caller holds further candidates (the order was only a prefix)
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs a) {
@@ -287,6 +509,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
                                // already be writing s_nk for its own turn while slower warps still test turn w's value)
 
     const int set = blockIdx.x;
+    if (a.gate && a.gate[set] == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* boxes = a.boxes + (size_t)set * a.set_stride;
     const int* order = a.order ? a.order + (size_t)set * a.order_stride : nullptr;
@@ -402,6 +625,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
 
     const int nk = s_nk;
     if (tid == 0 && a.num_out) a.num_out[set] = nk;
+    if (tid == 0 && a.retry) a.retry[set] = (a.more && nk < limit) ? 1 : 0;
     if (a.out_rois) {  // proposal_layer.py:129,153-161: [post,5] rows (frame, x1, y1, x2, y2), zero padded
         float* o = a.out_rois + (size_t)set * a.post * 5;
         for (int k = tid; k < a.post; k += kNmsThreads) {
@@ -415,6 +639,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
         }
     }
 }
+
 
 constexpr size_t kNmsSmemBytes = (size_t)(kNmsKeptSmem + kNmsThreads + 64) * (sizeof(float4) + sizeof(float));
 
@@ -432,6 +657,7 @@ struct NmsWs {
     int* order;
     float* scores;
     float* boxes;
+    int* retry;
     size_t bytes;
 };
 // `sort_n` > 0 adds the sort buffers (sort_n items per set); `decode` adds decoded boxes + scores.
@@ -449,14 +675,16 @@ static NmsWs carve_nms_ws(void* ws, int sets, int n, int sort_n, bool decode) {
         w.scores = cv.take<float>((size_t)sets * sort_n);
         w.boxes = cv.take<float>((size_t)sets * sort_n * 4);
     }
+    w.retry = cv.take<int>((size_t)sets);
     w.bytes = cv.used();
     return w;
 }
 
+// `gate`: per-segment flags; a segment whose flag is 0 is left alone
 static int launch_sort(const float* keys, int segments, int n, int key_stride, int64_t seg_stride, const NmsWs& w,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const int* gate = nullptr) {
     segment_sort_kernel<<<segments, kSortThreads, 0, stream>>>(keys, n, key_stride, seg_stride, w.sort_k, w.sort_i,
-                                                              w.order, n);
+                                                              w.order, n, gate);
     return check_launch("segment_sort_kernel");
 }
 
@@ -516,7 +744,10 @@ extern "C" int i2v_nms_dets(const float* dets, int num_boxes, float thresh, int*
         set_error("nms_dets: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
         return I2V_ERR_WORKSPACE;
     }
-    I2V_TRY(launch_sort(dets + 4, 1, num_boxes, 5, 0, w, stream));
+    if (num_boxes <= kTopK)   // the whole order in one short kernel
+        I2V_TRY(launch_topk_order(dets + 4, 1, num_boxes, 5, 0, w.order, num_boxes, num_boxes, stream));
+    else
+        I2V_TRY(launch_sort(dets + 4, 1, num_boxes, 5, 0, w, stream));
     NmsArgs a{};
     a.boxes = dets;
     a.box_stride = 5;
@@ -579,16 +810,21 @@ static int proposal_forward_impl(bool from_scores, const float* cls_prob, const 
         proposal_decode_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(cls_prob, bbox_pred, im_info, base_anchors, batch,
                                                                                 num_anchors, height, width, feat_stride, w.boxes, w.scores);
     I2V_TRY(check_launch("proposal_decode_kernel"));
-    I2V_TRY(launch_sort(w.scores, batch, ka, 1, ka, w, stream));
+    // proposal_layer.py:140-141: keep the pre_nms_topN best (the guard compares against the batch-wide numel, which
+    // for any batch reduces to min(pre_nms_topN, K*A) per frame)
+    const int n_cand = (pre_nms_top_n > 0 && pre_nms_top_n < ka) ? pre_nms_top_n : ka;
+    // Short path: order only the kTopK best scores of each frame and run NMS on those.  It is complete when they are all
+    // the candidates there are, and otherwise whenever NMS keeps post_nms_topN boxes before they run out (test mode: 300
+    // boxes are found within the first ~3 K candidates); a frame where it does not raises its retry flag and is redone
+    // by the full sort + NMS below, which skip every other frame.
+    static const bool no_short = getenv("I2V_PROPOSAL_FULL_SORT") != nullptr;
+    const bool short_path = !no_short && topk_order_ok(ka) && (n_cand <= kTopK || post_nms_top_n * 8 <= kTopK);
     NmsArgs a{};
     a.boxes = w.boxes;
     a.set_stride = (int64_t)ka * 4;
     a.box_stride = 4;
     a.order = w.order;
     a.order_stride = ka;
-    // proposal_layer.py:140-141: keep the pre_nms_topN best (the guard compares against the batch-wide numel, which
-    // for any batch reduces to min(pre_nms_topN, K*A) per frame)
-    a.n = (pre_nms_top_n > 0 && pre_nms_top_n < ka) ? pre_nms_top_n : ka;
     a.thresh = nms_thresh;
     a.max_keep = post_nms_top_n;
     a.num_out = out_counts;
@@ -598,7 +834,21 @@ static int proposal_forward_impl(bool from_scores, const float* cls_prob, const 
     a.post = post_nms_top_n;
     a.frame_base = frame_base;
     // the spill arrays are indexed by kept slot < a.n <= ka: carved for ka per frame
-    a.spill_box = w.spill_box;
+    if (short_path) {
+        I2V_TRY(launch_topk_order(w.scores, batch, ka, 1, ka, w.order, ka, n_cand, stream));
+        a.n = n_cand < kTopK ? n_cand : kTopK;
+        if (n_cand <= kTopK) return launch_nms(a, batch, stream);
+        a.more = 1;
+        a.retry = w.retry;
+        I2V_TRY(launch_nms(a, batch, stream));
+        a.more = 0;
+        a.retry = nullptr;
+        a.gate = w.retry;
+        I2V_TRY(launch_sort(w.scores, batch, ka, 1, ka, w, stream, w.retry));
+    } else {
+        I2V_TRY(launch_sort(w.scores, batch, ka, 1, ka, w, stream));
+    }
+    a.n = n_cand;
     return launch_nms(a, batch, stream);
 }
 

@@ -103,9 +103,9 @@ def test_decode_and_sort_stages(ops, orc, golden):
     assert np.array_equal(order.cpu().numpy()[0], np.argsort(-wsc[0], kind="stable"))
 
 
-def test_sort_is_stable_with_ties_and_negatives(ops):
+@pytest.mark.parametrize("n", [70, 4000, 4096, 5000])      # <= 4096: the top-K order kernel; above: the full radix sort
+def test_sort_is_stable_with_ties_and_negatives(ops, n):
     rng = np.random.default_rng(2)
-    n = 5000
     score = rng.choice(np.array([-2.5, -0.0, 0.0, 0.25, 0.25, 1e-30, 3.0, -1e-30], np.float32), n)
     dets = np.concatenate([rng.uniform(0, 100, (n, 4)).astype(np.float32), score[:, None]], 1)
     # thresh 2.0 > any IoU: nothing is suppressed, the keep list IS the sort order
@@ -144,6 +144,52 @@ def test_proposal_layer_module(ops, orc):
     assert np.array_equal(out.cpu().numpy(), orc.proposal_layer(cls, reg, info, 6000, 300, 0.7))
     out = layer((cuda(cls), cuda(reg), cuda(info), "TRAIN"), target=True)
     assert np.array_equal(out.cpu().numpy(), orc.proposal_layer(cls, reg, info, 12000, 128, 0.7))
+
+
+def _collapse(cls, reg, frame, how_many):
+    """The `how_many` best-scored anchors of `frame` regress onto ONE box (so NMS keeps a single one of them)."""
+    A = synth.NUM_ANCHORS
+    h, w = cls.shape[2:]
+    anchors = synth._anchors(h, w).astype(np.float64)
+    fg = cls[frame, A:].transpose(1, 2, 0).reshape(-1)
+    top = np.argsort(-fg, kind="stable")[:how_many]
+    aw, ah = anchors[top, 2] - anchors[top, 0] + 1, anchors[top, 3] - anchors[top, 1] + 1
+    acx, acy = anchors[top, 0] + 0.5 * aw, anchors[top, 1] + 0.5 * ah
+    d = reg[frame].transpose(1, 2, 0).reshape(-1, 4).copy()
+    d[top] = np.stack([(500.0 - acx) / aw, (300.0 - acy) / ah, np.log(200.0 / aw), np.log(150.0 / ah)], 1)
+    reg[frame] = d.reshape(h, w, A * 4).transpose(2, 0, 1)
+
+
+def test_proposal_short_order_runs_out_and_the_frame_is_redone(ops, orc):
+    # Frame 1: the 5000 best anchors collapse onto one box, so the 4096 ordered first yield a single kept box and the
+    # frame must be redone from the full order; frame 2: every anchor collapses (fewer than 300 boxes exist at all);
+    # frames 0 and 3 take the short path.  All four must equal the oracle, which always sorts everything.
+    cls, reg = synth.rpn_outputs(31, batch=4)
+    info = synth.im_info(4)
+    _collapse(cls, reg, 1, 5000)
+    _collapse(cls, reg, 2, cls.shape[2] * cls.shape[3] * synth.NUM_ANCHORS)
+    for pre, post in ((12000, 300), (6000, 300), (6000, 50)):
+        out, counts = ops.proposal_forward(cuda(cls), cuda(reg), cuda(info), cuda(synth.BASE_ANCHORS), 16, pre, post, 0.7,
+                                           return_counts=True)
+        want = orc.proposal_layer(cls, reg, info, pre, post, 0.7)
+        assert np.array_equal(out.cpu().numpy(), want)
+        c = counts.cpu().numpy()
+        assert c[0] == post and c[3] == post and c[2] < 10
+
+
+def test_proposal_short_order_with_ties_across_its_boundary(ops, orc):
+    # scores quantised to 32 levels: some 670 anchors share each value and one such run straddles rank 4096, where the
+    # selection must take exactly the lower-indexed ones (stable order of proposal_layer.py:127)
+    cls, reg = synth.rpn_outputs(32, batch=2)
+    info = synth.im_info(2)
+    A = synth.NUM_ANCHORS
+    cls[:, A:] = np.round(cls[:, A:] * 32) / 32
+    cls[:, :A] = 1.0 - cls[:, A:]
+    cls[1, A:] = 0.5                                                   # one frame with ALL scores equal
+    cls[1, :A] = 0.5
+    for pre, post in ((12000, 300), (3000, 300)):
+        out = ops.proposal_forward(cuda(cls), cuda(reg), cuda(info), cuda(synth.BASE_ANCHORS), 16, pre, post, 0.7)
+        assert np.array_equal(out.cpu().numpy(), orc.proposal_layer(cls, reg, info, pre, post, 0.7))
 
 
 def test_proposal_small_map_and_padding(ops, orc):
