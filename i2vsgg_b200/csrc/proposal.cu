@@ -519,11 +519,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
     const float thr = a.thresh;
     const int limit = a.max_keep > 0 ? a.max_keep : INT_MAX;
 
-    if (tid == 0) s_nk = 0;
+    __shared__ unsigned s_live[2];   // per chunk (double-buffered): bit w <=> warp w still has a candidate after step (a)
+    if (tid == 0) {
+        s_nk = 0;
+        s_live[0] = s_live[1] = 0u;
+    }
     __syncthreads();
     bool done = (a.n == 0);
 
-    for (int base = 0; base < a.n && !done; base += kNmsThreads) {
+    for (int base = 0, chunk = 0; base < a.n && !done; base += kNmsThreads, ++chunk) {
         const int i = base + tid;
         const bool have = i < a.n;
         int row = 0;
@@ -553,31 +557,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_scan_kernel(const NmsArgs 
             }
             if (alive && nms_suppressed(kb, ka, box, area, thr)) alive = false;
         }
+        const unsigned am0 = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0 && am0) atomicOr(&s_live[chunk & 1], 1u << warp);
         __syncthreads();
-        // (b) this warp's 32x32 suppression bitmask: bit j of `mask` <=> this lane's box removes lane j's (j > lane)
+        const unsigned live = s_live[chunk & 1];
+        if (tid == 0) s_live[(chunk + 1) & 1] = 0u;        // nobody touches the other buffer before the chunk ends
+        // (b) this warp's 32x32 suppression bitmask: bit j of `mask` <=> this lane's box removes lane j's (j > lane);
+        //     only candidates that are still there matter
         unsigned mask = 0;
-        if (__ballot_sync(0xffffffffu, alive) != 0u) {
-            for (int j = 0; j < 32; ++j) {
-                float4 ob = cbox[warp * 32 + j];
-                float oa = carea[warp * 32 + j];
-                if (alive && j > lane && nms_suppressed(box, area, ob, oa, thr)) mask |= 1u << j;
-            }
+        for (unsigned todo = am0; todo; todo &= todo - 1u) {
+            const int j = __ffs(todo) - 1;
+            float4 ob = cbox[warp * 32 + j];
+            float oa = carea[warp * 32 + j];
+            if (alive && j > lane && nms_suppressed(box, area, ob, oa, thr)) mask |= 1u << j;
         }
-        // (c) warps take their turn in candidate order
+        // (c) warps take their turn in candidate order; a warp with nothing left after (a) has no turn
+        int turn = 0;
         for (int w = 0; w < kNmsWarps; ++w) {
-            const int pb = w & 1;
+            if (!((live >> w) & 1u)) continue;
+            const int pb = turn++ & 1;
             if (warp == w) {
                 const int nk = s_nk;
-                unsigned am = __ballot_sync(0xffffffffu, alive);
-                unsigned keepm = 0, remv = 0;
-                if (am) {
-                    for (int l = 0; l < 32; ++l) {
-                        unsigned ml = __shfl_sync(0xffffffffu, mask, l);
-                        if (((am >> l) & 1u) && !((remv >> l) & 1u)) {
-                            keepm |= 1u << l;
-                            remv |= ml;
-                        }
-                    }
+                unsigned rem = __ballot_sync(0xffffffffu, alive), keepm = 0;
+                while (rem) {                              // one step per KEPT box: the lowest survivor stays, its mask goes
+                    const int l = __ffs(rem) - 1;
+                    keepm |= 1u << l;
+                    rem &= ~(__shfl_sync(0xffffffffu, mask, l) | (1u << l));
                 }
                 int cnt = __popc(keepm);
                 const int room = limit - nk;
