@@ -387,9 +387,24 @@ int roi_pool_rows_plane(const float* features, const float* rois, void* out, int
     if (out_dtype == I2V_DT_BF16 && channels % kKB == 0 && !getenv("I2V_POOL_F32_PLANES") &&
         plane_bf16_smem_bytes(height, width) <= (size_t)kMaxSmemPerCta) {
         // bf16 planes, two channels per word: half the instructions; CTAs sized to fill whole waves
+        // RoI slices per (frame, channel tile): the CTAs should fill whole waves of the 148 SMs (a CTA per SM: the planes
+        // take 158 KB) while a slice keeps enough RoIs per warp to pay for its fill
         const int tiles = batch * (channels / kKB);
-        int split = max(1, (2 * kNumSMs) / tiles);
-        while (split > 1 && (split - 1) * kWarps >= num_rois) --split;
+        int split = 1;
+        {
+            double best = 0.0;
+            const int per_frame = max(1, num_rois / batch);
+            for (int sp = 1; sp <= 16; ++sp) {
+                if (sp > 1 && per_frame / (sp * kWarps) < 8) break;
+                const double waves = (double)tiles * sp / kNumSMs;
+                const double eff = waves / ceil(waves) - 0.004 * sp;   // a fill costs about 0.4 % of a two-slice CTA
+                if (eff > best) {
+                    best = eff;
+                    split = sp;
+                }
+            }
+            if (const char* e = getenv("I2V_POOL_SPLIT")) split = max(1, atoi(e));
+        }
         const size_t smem = plane_bf16_smem_bytes(height, width);
         dim3 grid((unsigned)(tiles * split));
         if (pool_pitch_for(width) == 41) {
