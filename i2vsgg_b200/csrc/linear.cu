@@ -536,6 +536,112 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
     }
 }
 
+
+// Tiled variant: lanes own predicates (r = lane + 32 j), a warp works on eight rows of x at a time, and the dot products
+// run over E with the predicate table TRANSPOSED in shared memory ([E][RP], RP = R rounded up to 32, zero padded, written
+// that way by the normalisation kernel): per element of E a warp issues RP/32 conflict-free shared loads that feed
+// 8 x RP/32 FMAs, the eight x values arriving as broadcast 16-byte loads.  No cross-lane reduction is left in the dot
+// products; only the norms and the softmax use shuffles.  One persistent CTA per SM keeps the table for all its rows.
+constexpr int kTileRows = 8;
+constexpr int kTileWarps = 16;
+template <int J>    // RP / 32
+__global__ void __launch_bounds__(kTileWarps * 32, 1)
+    rel_score_tile_kernel(const float* __restrict__ x, const float* __restrict__ prdT, float* __restrict__ scores, int P, int R,
+                          int E, int apply_softmax) {
+    extern __shared__ __align__(16) float sc_smem[];   // [E][32 J]
+    constexpr int RP = 32 * J;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < E * RP / 4; i += kTileWarps * 32)
+        reinterpret_cast<float4*>(sc_smem)[i] = __ldg(reinterpret_cast<const float4*>(prdT) + i);
+    __syncthreads();
+    const int tiles = (P + kTileRows - 1) / kTileRows;
+    for (int tile = blockIdx.x * kTileWarps + warp; tile < tiles; tile += gridDim.x * kTileWarps) {
+        const int row0 = tile * kTileRows;
+        const float* xr[kTileRows];
+        float inv[kTileRows];
+#pragma unroll
+        for (int q = 0; q < kTileRows; ++q) {
+            xr[q] = x + (size_t)min(row0 + q, P - 1) * E;            // a ragged tail recomputes the last row (never stored)
+            float ss = 0.f;
+            for (int i = lane; i < E; i += 32) {
+                const float v = __ldg(xr[q] + i);
+                ss = fmaf(v, v, ss);
+            }
+            for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            inv[q] = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        }
+        float acc[kTileRows][J];
+#pragma unroll
+        for (int q = 0; q < kTileRows; ++q)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[q][j] = 0.f;
+        const float* ps = sc_smem + lane;
+#pragma unroll 1
+        for (int e4 = 0; e4 < E / 4; ++e4) {
+            float4 xv[kTileRows];
+#pragma unroll
+            for (int q = 0; q < kTileRows; ++q) xv[q] = __ldg(reinterpret_cast<const float4*>(xr[q]) + e4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float pv[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) pv[j] = ps[(e4 * 4 + t) * RP + 32 * j];
+#pragma unroll
+                for (int q = 0; q < kTileRows; ++q) {
+                    const float xq = t == 0 ? xv[q].x : t == 1 ? xv[q].y : t == 2 ? xv[q].z : xv[q].w;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) acc[q][j] = fmaf(xq, pv[j], acc[q][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kTileRows; ++q) {
+            const int row = row0 + q;
+            if (row >= P) break;
+            float* out = scores + (size_t)row * R;
+            float sv[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) sv[j] = acc[q][j] * inv[q];
+            if (apply_softmax) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (lane + 32 * j < R) mx = fmaxf(mx, sv[j]);
+                for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    sv[j] = lane + 32 * j < R ? expf(sv[j] - mx) : 0.f;
+                    sum += sv[j];
+                }
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+                for (int j = 0; j < J; ++j) sv[j] = sv[j] / sum;
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (lane + 32 * j < R) out[lane + 32 * j] = sv[j];
+        }
+    }
+}
+
+// normalised predicate embeddings, transposed and zero padded: dst [cols][rp], rp >= rows
+__global__ void __launch_bounds__(256) l2_normalize_rows_t_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                  int rows, int cols, int rp) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rp) return;
+    if (row >= rows) {
+        for (int i = lane; i < cols; i += 32) dst[(size_t)i * rp + row] = 0.f;
+        return;
+    }
+    const float* s = src + (size_t)row * cols;
+    float acc = 0.f;
+    for (int i = lane; i < cols; i += 32) acc += s[i] * s[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+    for (int i = lane; i < cols; i += 32) dst[(size_t)i * rp + row] = s[i] * inv;
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -661,7 +767,7 @@ extern "C" int i2v_cast_bf16(const float* src, void* dst, long long rows, long l
 
 extern "C" size_t i2v_rel_scores_workspace_bytes(int num_rel, int emb_dim) {
     if (num_rel < 0 || emb_dim < 0) return 0;
-    return align_up((size_t)num_rel * emb_dim * sizeof(float), 256);
+    return align_up((size_t)align_up((size_t)num_rel, 32) * emb_dim * sizeof(float), 256);   // rows padded to 32 (tiled kernel)
 }
 
 extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, int num_pairs, int num_rel, int emb_dim,
@@ -675,6 +781,32 @@ extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, i
         return I2V_ERR_WORKSPACE;
     }
     float* prdn = static_cast<float*>(workspace);
+    {   // tiled kernel: transposed table in shared memory, as many predicates per lane as the template holds
+        const int rp = (int)align_up((size_t)num_rel, 32), J = rp / 32;
+        const size_t table = (size_t)emb_dim * rp * sizeof(float);
+        if (J <= 5 && emb_dim % 4 == 0 && table <= (size_t)kMaxSmemPerCta && ((uintptr_t)x & 15) == 0 &&
+            num_pairs >= 64 && !getenv("I2V_REL_SCORE_ROWS")) {
+            l2_normalize_rows_t_kernel<<<ceil_div(rp, 8), 256, 0, stream>>>(prd, prdn, num_rel, emb_dim, rp);
+            I2V_TRY(check_launch("l2_normalize_rows_t_kernel"));
+            const int tiles = ceil_div(num_pairs, kTileRows);
+            const int grid = min(kNumSMs, ceil_div(tiles, kTileWarps));
+#define I2V_SCORE_TILE(JJ)                                                                                              \
+    do {                                                                                                                \
+        auto kern = rel_score_tile_kernel<JJ>;                                                                          \
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table));              \
+        kern<<<grid, kTileWarps * 32, table, stream>>>(x, prdn, scores, num_pairs, num_rel, emb_dim, apply_softmax);    \
+    } while (0)
+            switch (J) {
+                case 1: I2V_SCORE_TILE(1); break;
+                case 2: I2V_SCORE_TILE(2); break;
+                case 3: I2V_SCORE_TILE(3); break;
+                case 4: I2V_SCORE_TILE(4); break;
+                default: I2V_SCORE_TILE(5); break;
+            }
+#undef I2V_SCORE_TILE
+            return check_launch("rel_score_tile_kernel");
+        }
+    }
     l2_normalize_rows_kernel<<<ceil_div(num_rel, 8), 256, 0, stream>>>(prd, prdn, num_rel, emb_dim);
     I2V_TRY(check_launch("l2_normalize_rows_kernel"));
     size_t smem = (size_t)kScoreWarps * kScoreRows * ((size_t)emb_dim + num_rel) * sizeof(float);

@@ -100,7 +100,9 @@ def test_cast_bf16_is_round_to_nearest_even(ops):
     assert torch.equal(ops.cast_bf16(wide[:, 100:228]), wide[:, 100:228].bfloat16())
 
 
-@pytest.mark.parametrize("p,r,e", [(4032, 132, 300), (7, 5, 33), (1, 132, 300)])
+# the tiled kernel (>= 64 rows, E % 4 == 0, R <= 160) with full and ragged row tiles, and the row-per-warp kernel
+@pytest.mark.parametrize("p,r,e", [(4032, 132, 300), (4035, 132, 300), (100, 40, 64), (65, 160, 8), (7, 5, 33), (1, 132, 300),
+                                   (70, 161, 12)])
 def test_rel_scores_match_torch(ops, p, r, e):
     g = torch.Generator(device="cuda").manual_seed(p + r)
     x = torch.randn((p, e), device="cuda", generator=g)
