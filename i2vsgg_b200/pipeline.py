@@ -64,8 +64,9 @@ class HostPipeline:
                                    dtype=torch.uint8, device=device)
         self.ws_roi = torch.empty(self.lib.i2v_roi_align_workspace_bytes(frames, self.N), dtype=torch.uint8,
                                   device=device)
-        # kernels per step: decode, sort, nms | prep, bucket, forward | prep, bucket, phase tables, backward (memsets not counted)
-        self.launches_per_step = 10
+        # kernels per step: decode, top-K order, nms, gated full sort, gated nms | prep, bucket, slab tables, forward |
+        # prep, bucket, phase tables, backward (memsets not counted)
+        self.launches_per_step = 13
         self._host = None
 
     # ------------------------------------------------------------------ device-resident inputs
@@ -105,12 +106,15 @@ class HostPipeline:
     def pipelined_step(self, cls_prob, bbox_pred, im_info, features, grad_out, next_rpn=None):
         """One step whose proposal layer was (or is now) launched on a second stream, and which launches the NEXT
         batch's proposal layer (`next_rpn = (cls_prob, bbox_pred, im_info)`) on that stream before its own RoIAlign
-        backward.  The proposal chain is latency-bound (one CTA per frame, 0.36 ms on 32 of 148 SMs); its CTAs slot in
+        backward.  The proposal chain is latency-bound (1-4 CTAs per frame, 0.25 ms on at most 128 of 148 SMs); its CTAs slot in
         between the waves of the backward kernel instead of holding the whole GPU.  Every step still runs all three
         stages; only their placement in time changes.  Returns (rois, pooled, grad_in) of THIS step."""
         main = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream(self.dev)
+            # high priority: when an SM frees up under the backward kernel (one 227 KB CTA per SM, many waves) the
+            # proposal chain's CTAs are placed before the backward's next CTA, so the chain really runs underneath it
+            # instead of at its tail
+            self._side = torch.cuda.Stream(self.dev, priority=-1)
         if self._pending is None:                      # first step of a run: nothing was launched ahead
             self._side.wait_stream(main)
             self._launch_proposal(cls_prob, bbox_pred, im_info, self._rois_pp[0], self._side)
