@@ -163,15 +163,36 @@ class HostPipeline:
         Frames are independent, so the batch moves in chunks of `chunk_frames`: chunk k+1 is on its way in (copy
         engine 1) while chunk k computes and chunk k-1 is on its way out (copy engine 2).  The PCIe link is full duplex,
         which makes the step cost max(bytes in, bytes out) / link instead of their sum."""
+        out = self.host_step_async(cls_prob, bbox_pred, im_info, features, grad_out, chunk_frames, slot=0)
+        out[3].synchronize()
+        return out[:3]
+
+    def host_step_async(self, cls_prob, bbox_pred, im_info, features, grad_out, chunk_frames: int = 4, slot: int = 0):
+        """`host_step` without the final wait: returns (rois_h, pooled_h, grad_in_h, event); the results are in the host
+        buffers of `slot` (0 or 1) once `event.synchronize()` returns.  A caller that keeps two steps in flight -- issue
+        step i+1 into the other slot, then wait for step i -- lets the inputs of a step travel in while the results of
+        the step before are still on their way out, so that the link's two directions stay busy across step boundaries
+        (the first chunk in and the last chunk out of a step are otherwise alone on the link).  Device buffers are
+        shared between the steps; per-chunk events keep a chunk's input from being overwritten before its compute has
+        read it, and its result from being overwritten before the copy out of the step before has read it."""
         d = self._host_buffers(cls_prob, bbox_pred, im_info, features, grad_out)
+        if slot and "rois_h1" not in d:
+            for k in ("rois_h", "pooled_h", "grad_in_h"):
+                d[k + "1"] = torch.empty(d[k].shape, dtype=torch.float32).pin_memory()
+        sfx = "1" if slot else ""
+        rois_h, pooled_h, grad_in_h = d["rois_h" + sfx], d["pooled_h" + sfx], d["grad_in_h" + sfx]
         main, s_in, s_out = torch.cuda.current_stream(), d["s_in"], d["s_out"]
-        s_in.wait_stream(main)
-        s_out.wait_stream(main)
+        computed, copied = d.setdefault("computed", {}), d.setdefault("copied", {})
+        if not computed:            # first use: order the copy streams after whatever the caller did before
+            s_in.wait_stream(main)
+            s_out.wait_stream(main)
         post = self.post
         for f0 in range(0, self.B, chunk_frames):
             f1 = min(self.B, f0 + chunk_frames)
             r0, r1 = f0 * post, f1 * post
             with torch.cuda.stream(s_in):
+                if f0 in computed:
+                    s_in.wait_event(computed[f0])          # the step before has read this chunk's device inputs
                 d["cls"][f0:f1].copy_(cls_prob[f0:f1], non_blocking=True)
                 d["reg"][f0:f1].copy_(bbox_pred[f0:f1], non_blocking=True)
                 d["info"][f0:f1].copy_(im_info[f0:f1], non_blocking=True)
@@ -179,20 +200,21 @@ class HostPipeline:
                 d["grad"][r0:r1].copy_(grad_out[r0:r1], non_blocking=True)
                 ready = s_in.record_event()
             main.wait_event(ready)
+            if f0 in copied:
+                main.wait_event(copied[f0])                # the step before has copied this chunk's results out
             self._run(d["cls"][f0:f1], d["reg"][f0:f1], d["info"][f0:f1], d["feat"][f0:f1], d["grad"][r0:r1],
                       self.rois[f0:f1], self.pooled[r0:r1], self.grad_in[f0:f1], f1 - f0)
             if f0:      # frame indices of the whole batch, as device_step writes them
                 check(self.lib.i2v_rois_add_frame(_p(self.rois[f0:f1]), (f1 - f0) * post, f0,
                                                   ctypes.c_void_p(main.cuda_stream)), "rois_add_frame")
-            done = main.record_event()
+            done = computed[f0] = main.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
-                d["rois_h"][f0:f1].copy_(self.rois[f0:f1], non_blocking=True)
-                d["pooled_h"][r0:r1].copy_(self.pooled[r0:r1], non_blocking=True)
-                d["grad_in_h"][f0:f1].copy_(self.grad_in[f0:f1], non_blocking=True)
-        main.wait_stream(s_out)
-        main.synchronize()
-        return d["rois_h"], d["pooled_h"], d["grad_in_h"]
+                rois_h[f0:f1].copy_(self.rois[f0:f1], non_blocking=True)
+                pooled_h[r0:r1].copy_(self.pooled[r0:r1], non_blocking=True)
+                grad_in_h[f0:f1].copy_(self.grad_in[f0:f1], non_blocking=True)
+                copied[f0] = s_out.record_event()
+        return rois_h, pooled_h, grad_in_h, copied[f0]
 
     h2d_bytes = 0
     d2h_bytes = 0
