@@ -39,29 +39,37 @@ __device__ __forceinline__ void bulk_store_commit(void* gdst, const void* ssrc, 
 __device__ __forceinline__ void put(float* p, float v) { *p = v; }
 __device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// One sweep over the columns [x, x_end) of a bin row that is NR rows tall (NR <= 8).  Half-warp 0 owns rows 0, 2, ...,
-// half-warp 1 rows 1, 3, ... of the bin row: NR/2 loads at compile-time offsets for both halves, plus -- for odd NR -- one
-// more at `tail` (the extra row of half 0; half 1 re-reads its last row, which cannot change a maximum).  No lane-dependent
-// control flow.  Bins tile the columns with at most one shared column, whose value is carried into the next bin.
+// One sweep over the columns of a bin row that is NR rows tall (NR <= 12).  Half-warp 0 owns rows 0, 2, ..., half-warp 1
+// rows 1, 3, ... of the bin row: NR/2 loads at compile-time offsets for both halves, plus -- for odd NR -- one more at
+// `tail` (the extra row of half 0; half 1 re-reads its last row, which cannot change a maximum).  No lane-dependent
+// control flow.  Bins tile the columns with at most one shared column, whose value is carried into the next bin: `we[pw]`
+// is the end column of bin pw and bit pw of `shared` says that bin pw + 1 starts on bin pw's last column; both are the
+// same for the seven bin rows of a RoI and live in registers (the bin loop is unrolled), and the cross-half maxima and
+// the stores of the row's seven bins are issued together at the end.
 template <int NR, int kPitch, typename OutT>
-__device__ __forceinline__ void sweep_bin_row(const float* p, int tail, int x, int lo, int hi, int half, OutT* dst) {
+__device__ __forceinline__ void sweep_bin_row(const float* p, int tail, int x, const int (&we)[7], unsigned shared, int half,
+                                              OutT* dst) {
     constexpr int kRow2 = 2 * kPitch * kK;
     float v = -FLT_MAX, carry = -FLT_MAX;
-#pragma unroll 1
+    float best[7];
+#pragma unroll
     for (int pw = 0; pw < 7; ++pw) {
-        const int we = __shfl_sync(0xffffffffu, hi, 7 + pw);
-        const int ws_next = __shfl_sync(0xffffffffu, lo, 7 + min(pw + 1, 6));
-        float best = carry;
+        float b = carry;
 #pragma unroll 2
-        for (; x < we; ++x, p += kK) {          // the tight part: loads and maxima only
+        for (; x < we[pw]; ++x, p += kK) {      // the tight part: loads and maxima only
             v = (NR & 1) ? p[tail] : -FLT_MAX;
 #pragma unroll
             for (int k = 0; k < NR / 2; ++k) v = fmaxf(v, p[k * kRow2]);
-            best = fmaxf(best, v);
+            b = fmaxf(b, v);
         }
-        const float r = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 16));
-        if (half == 0) put(dst + pw, r);
-        carry = (pw < 6 && ws_next == we - 1) ? v : -FLT_MAX;   // `v` is the bin's last column
+        best[pw] = b;
+        carry = ((shared >> pw) & 1u) ? v : -FLT_MAX;   // `v` is the bin's last column
+    }
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) best[pw] = fmaxf(best[pw], __shfl_xor_sync(0xffffffffu, best[pw], 16));
+    if (half == 0) {
+#pragma unroll
+        for (int pw = 0; pw < 7; ++pw) put(dst + pw, best[pw]);
     }
 }
 
@@ -128,6 +136,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             const unsigned nonempty = __ballot_sync(0xffffffffu, hi > lo);
             const unsigned tiles = __ballot_sync(0xffffffffu, next_lo >= hi - 1 && next_lo <= hi);
             const bool regular = ((nonempty >> 7) & 0x7fu) == 0x7fu && ((tiles >> 7) & 0x3fu) == 0x3fu;
+            int we[7];                                // the bin columns' end, and which bins share a column with the next
+#pragma unroll
+            for (int pw = 0; pw < 7; ++pw) we[pw] = __shfl_sync(0xffffffffu, hi, 7 + pw);
+            const unsigned shared = (__ballot_sync(0xffffffffu, next_lo == hi - 1) >> 7) & 0x3fu;
 #pragma unroll 1
             for (int ph = 0; ph < 7; ++ph) {
                 const int hs = __shfl_sync(0xffffffffu, lo, ph), he = __shfl_sync(0xffffffffu, hi, ph);
@@ -150,18 +162,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float* p = rowp + (size_t)x0 * kK;
                     const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;
                     switch (nr) {   // uniform
-                        case 1: sweep_bin_row<1, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 2: sweep_bin_row<2, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 3: sweep_bin_row<3, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 4: sweep_bin_row<4, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 5: sweep_bin_row<5, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 6: sweep_bin_row<6, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 7: sweep_bin_row<7, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 8: sweep_bin_row<8, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 9: sweep_bin_row<9, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 10: sweep_bin_row<10, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        case 11: sweep_bin_row<11, kPitch>(p, tail, x0, lo, hi, half, dst); break;
-                        default: sweep_bin_row<12, kPitch>(p, tail, x0, lo, hi, half, dst); break;
+                        case 1: sweep_bin_row<1, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 2: sweep_bin_row<2, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 3: sweep_bin_row<3, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 4: sweep_bin_row<4, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 5: sweep_bin_row<5, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 6: sweep_bin_row<6, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 7: sweep_bin_row<7, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 8: sweep_bin_row<8, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 9: sweep_bin_row<9, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 10: sweep_bin_row<10, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        case 11: sweep_bin_row<11, kPitch>(p, tail, x0, we, shared, half, dst); break;
+                        default: sweep_bin_row<12, kPitch>(p, tail, x0, we, shared, half, dst); break;
                     }
                 } else {
 #pragma unroll 1
@@ -205,30 +217,37 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
     return r;
 }
 
-// `p` points at the lane's word (16 words per cell); dst_lo / dst_hi are the staging rows of its two channels
+// `p` points at the lane's word (16 words per cell) in column `x`; dst_lo / dst_hi are the staging rows of its two channels.
+// `we[pw]` is the end column of bin pw and bit pw of `shared` says that bin pw + 1 starts on bin pw's last column; both are
+// the same for the seven bin rows of a RoI and live in registers (the bin loop is unrolled), so a bin costs its loads and
+// maxima plus one shuffle and two stores, which are issued together after the row's seven bins.
 template <int NR, int kPitch>
-__device__ __forceinline__ void sweep_bin_row_bf16(const unsigned* p, int tail, int x, int lo, int hi, int half,
-                                                   unsigned short* dst_lo, unsigned short* dst_hi) {
+__device__ __forceinline__ void sweep_bin_row_bf16(const unsigned* p, int tail, int x, const int (&we)[7], unsigned shared,
+                                                   int half, unsigned short* dst_lo, unsigned short* dst_hi) {
     constexpr int kRow2 = 2 * kPitch * 16;
     unsigned v = kNegInf2, carry = kNegInf2;
-#pragma unroll 1
+    unsigned best[7];
+#pragma unroll
     for (int pw = 0; pw < 7; ++pw) {
-        const int we = __shfl_sync(0xffffffffu, hi, 7 + pw);
-        const int ws_next = __shfl_sync(0xffffffffu, lo, 7 + min(pw + 1, 6));
-        unsigned best = carry;
+        unsigned b = carry;
 #pragma unroll 2
-        for (; x < we; ++x, p += 16) {          // the tight part: loads and maxima only
+        for (; x < we[pw]; ++x, p += 16) {      // the tight part: loads and maxima only
             v = (NR & 1) ? p[tail] : kNegInf2;
 #pragma unroll
             for (int k = 0; k < NR / 2; ++k) v = hmax2(v, p[k * kRow2]);
-            best = hmax2(best, v);
+            b = hmax2(b, v);
         }
-        const unsigned r = hmax2(best, __shfl_xor_sync(0xffffffffu, best, 16));
-        if (half == 0) {
-            dst_lo[pw] = (unsigned short)(r & 0xffffu);
-            dst_hi[pw] = (unsigned short)(r >> 16);
+        best[pw] = b;
+        carry = ((shared >> pw) & 1u) ? v : kNegInf2;   // `v` is the bin's last column
+    }
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) best[pw] = hmax2(best[pw], __shfl_xor_sync(0xffffffffu, best[pw], 16));
+    if (half == 0) {
+#pragma unroll
+        for (int pw = 0; pw < 7; ++pw) {
+            dst_lo[pw] = (unsigned short)(best[pw] & 0xffffu);
+            dst_hi[pw] = (unsigned short)(best[pw] >> 16);
         }
-        carry = (pw < 6 && ws_next == we - 1) ? v : kNegInf2;   // `v` is the bin's last column
     }
 }
 
@@ -306,6 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             const unsigned nonempty = __ballot_sync(0xffffffffu, hi > lo);
             const unsigned tiles = __ballot_sync(0xffffffffu, next_lo >= hi - 1 && next_lo <= hi);
             const bool regular = ((nonempty >> 7) & 0x7fu) == 0x7fu && ((tiles >> 7) & 0x3fu) == 0x3fu;
+            int we[7];                                // the bin columns' end, and which bins share a column with the next
+#pragma unroll
+            for (int pw = 0; pw < 7; ++pw) we[pw] = __shfl_sync(0xffffffffu, hi, 7 + pw);
+            const unsigned shared = (__ballot_sync(0xffffffffu, next_lo == hi - 1) >> 7) & 0x3fu;
 #pragma unroll 1
             for (int ph = 0; ph < 7; ++ph) {
                 const int hs = __shfl_sync(0xffffffffu, lo, ph), he = __shfl_sync(0xffffffffu, hi, ph);
@@ -325,18 +348,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const unsigned* p = rowp + (size_t)x0 * 16;
                     const int tail = (half == 0 ? nr / 2 : max(nr / 2 - 1, 0)) * kRow2;
                     switch (nr) {   // uniform
-                        case 1: sweep_bin_row_bf16<1, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 2: sweep_bin_row_bf16<2, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 3: sweep_bin_row_bf16<3, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 4: sweep_bin_row_bf16<4, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 5: sweep_bin_row_bf16<5, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 6: sweep_bin_row_bf16<6, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 7: sweep_bin_row_bf16<7, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 8: sweep_bin_row_bf16<8, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 9: sweep_bin_row_bf16<9, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 10: sweep_bin_row_bf16<10, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        case 11: sweep_bin_row_bf16<11, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
-                        default: sweep_bin_row_bf16<12, kPitch>(p, tail, x0, lo, hi, half, dst_lo, dst_hi); break;
+                        case 1: sweep_bin_row_bf16<1, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 2: sweep_bin_row_bf16<2, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 3: sweep_bin_row_bf16<3, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 4: sweep_bin_row_bf16<4, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 5: sweep_bin_row_bf16<5, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 6: sweep_bin_row_bf16<6, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 7: sweep_bin_row_bf16<7, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 8: sweep_bin_row_bf16<8, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 9: sweep_bin_row_bf16<9, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 10: sweep_bin_row_bf16<10, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        case 11: sweep_bin_row_bf16<11, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
+                        default: sweep_bin_row_bf16<12, kPitch>(p, tail, x0, we, shared, half, dst_lo, dst_hi); break;
                     }
                 } else {
 #pragma unroll 1

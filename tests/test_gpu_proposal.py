@@ -240,6 +240,34 @@ def test_host_pipeline_chunked_copy_equals_device_step():
             assert torch.equal(a, b.cpu())
 
 
+def test_host_pipeline_two_steps_in_flight():
+    """`host_step_async` with step i+1 issued before step i is awaited (alternating result slots, shared device buffers)
+    returns, for a sequence of DIFFERENT batches, exactly what the device-resident step computes for each."""
+    from i2vsgg_b200.pipeline import HostPipeline
+    frames, ch = 6, 32
+    dev = torch.device("cuda", 0)
+    pipe = HostPipeline(dev, frames, ch, 38, 63, 7, 1 / 16, 3000, 50, 0.7)
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for k in range(4):
+        cls, reg = synth.rpn_outputs(90 + k, batch=frames)
+        feat = torch.randn((frames, ch, 38, 63), generator=g)
+        grad = torch.randn((frames * 50, ch, 7, 7), generator=g)
+        batches.append(tuple(t.pin_memory() for t in (torch.from_numpy(cls), torch.from_numpy(reg),
+                                                      torch.from_numpy(synth.im_info(frames)), feat, grad)))
+    want = [[t.cpu().clone() for t in pipe.device_step(*(t.to(dev) for t in b))] for b in batches]
+    prev, checked = None, 0
+    for k, b in enumerate(batches + [None]):
+        cur = pipe.host_step_async(*b, chunk_frames=2, slot=k & 1) if b is not None else None
+        if prev is not None:
+            prev[1][3].synchronize()
+            for a, w in zip(prev[1][:3], want[prev[0]]):
+                assert torch.equal(a, w)
+            checked += 1
+        prev = (k, cur) if cur is not None else None
+    assert checked == len(batches)
+
+
 def test_pipelined_step_equals_device_step():
     """The software-pipelined step (proposal of the next batch on a second stream) returns what the plain step returns,
     for a sequence of DIFFERENT batches."""
