@@ -65,6 +65,8 @@ SIGNATURES = {
     "i2v_pair_rows_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
     "i2v_conv2d_nhwc_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _i, _i, _vp]),
     "i2v_pair_conv1_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "i2v_pair_conv1_split_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "i2v_conv2d_nhwc_split_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _i, _i, _vp]),
     "i2v_gather_rows_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _vp]),
     "i2v_roi_gt_overlaps": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "i2v_fg_bg_select": (_i, [_vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),

@@ -74,6 +74,14 @@ __device__ __forceinline__ void tma_load_4d(void* sdst, const CUtensorMap* map, 
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+            smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -190,11 +198,16 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int q, int lan
 // element strides are the convolution's stride; k-block kb is channel chunk kb % chunks of filter tap kb / chunks, and the
 // 128 tile rows are `rows_per_image` output positions of 128 / rows_per_image consecutive images.  The TMA zero-fills the
 // padding border and the channel padding, so no patch matrix is ever written.
+// SPLIT (stride 2 only): the activation is stored as four parity planes per image, [N, 2, 2, H/2, W/2, C] (plane
+// (y & 1, x & 1), position (y >> 1, x >> 1)), seen through a 5-D map with unit element strides; the samples 2 o + k - pad of
+// tap k are then the DENSE box of plane (k - pad) & 1 at offset (k - pad) >> 1.  The strided 4-D box makes the TMA walk
+// every position it skips (the layer ran at 42 % of the tensor peak, waiting for its A tiles); the dense one does not.
 struct ConvGeom {
     int chunks;          // 64-channel chunks per tap
     int kw;              // filter width (taps per filter row)
     int pad;
     int rows_per_image;  // OH * OW
+    int split;           // 1: parity-split activation
 };
 
 template <int KIND, int BN, bool CONV = false>
@@ -253,7 +266,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (CONV) {
                     const int tap = kb / cg.chunks, chunk = kb - tap * cg.chunks;
                     const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
-                    tma_load_4d(a, &map_x, chunk * ELEMS, kx - cg.pad, ky - cg.pad, m0 / cg.rows_per_image, full + s);
+                    const int dx = kx - cg.pad, dy = ky - cg.pad;
+                    if (cg.split)
+                        tma_load_5d(a, &map_x, chunk * ELEMS, dx >> 1, dy >> 1, ((dy & 1) << 1) | (dx & 1),
+                                    m0 / cg.rows_per_image, full + s);
+                    else
+                        tma_load_4d(a, &map_x, chunk * ELEMS, dx, dy, m0 / cg.rows_per_image, full + s);
                 } else {
                     tma_load_2d(a, &map_x, kb * ELEMS, m0, full + s);
                 }
@@ -827,18 +845,20 @@ extern "C" int i2v_rel_scores(const float* x, const float* prd, float* scores, i
 
 // conv_lo's strided layers as an implicit GEMM (resnet_SGG_emb.py:107-110): x [N,H,W,C] bf16 NHWC, w [O, KH*KW*Cp] bf16
 // with every tap's channels padded to Cp = 64 * ceil(C / 64), y [N*OH*OW, O] (NHWC of the next layer).
-extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
-                                       int channels, int out_channels, int kernel, int stride, int pad, long long ldw,
-                                       long long ldy, int out_dtype, int relu, cudaStream_t stream) {
+static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
+                            int channels, int out_channels, int kernel, int stride, int pad, long long ldw, long long ldy,
+                            int out_dtype, int relu, bool split, cudaStream_t stream) {
     I2V_REQUIRE(n >= 0 && height >= 1 && width >= 1 && channels >= 1 && out_channels >= 1 && kernel >= 1 && stride >= 1 &&
                     pad >= 0,
                 "conv2d_nhwc: bad shape");
     I2V_REQUIRE(out_dtype == I2V_DT_BF16 || out_dtype == I2V_DT_F32, "conv2d_nhwc: out_dtype %d", out_dtype);
     const int OH = (height + 2 * pad - kernel) / stride + 1, OW = (width + 2 * pad - kernel) / stride + 1;
     const int rows = OH * OW, chunks = ceil_div(channels, 64), K = kernel * kernel * chunks * 64;
-    const bool ok = OH >= 1 && OW >= 1 && rows <= kBM && kBM % rows == 0 && channels % 8 == 0 && out_channels <= 128 &&
-                    OW * stride <= 256 && OH * stride <= 256 && ldw >= K && (ldw * 2) % 16 == 0 &&
-                    ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0;
+    bool ok = OH >= 1 && OW >= 1 && rows <= kBM && kBM % rows == 0 && channels % 8 == 0 && out_channels <= 128 &&
+              OW * stride <= 256 && OH * stride <= 256 && ldw >= K && (ldw * 2) % 16 == 0 && ((uintptr_t)x & 15) == 0 &&
+              ((uintptr_t)w & 15) == 0;
+    if (split)   // parity planes: stride 2, even map, "same" padding of an odd kernel, output = one plane's size
+        ok = ok && stride == 2 && height % 2 == 0 && width % 2 == 0 && OH == height / 2 && OW == width / 2;
     if (!ok) {
         set_error("conv2d_nhwc: needs OH*OW dividing 128, C %% 8 == 0, at most 128 output channels and 16-byte aligned rows");
         return I2V_ERR_UNSUPPORTED;
@@ -851,7 +871,21 @@ extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float
         return I2V_ERR_CUDA;
     }
     alignas(64) CUtensorMap map_x, map_w;
-    {
+    if (split) {
+        const int per_tile = kBM / rows;
+        const cuuint64_t plane = (cuuint64_t)OH * OW * channels * 2;
+        cuuint64_t dims[5] = {(cuuint64_t)channels, (cuuint64_t)OW, (cuuint64_t)OH, 4, (cuuint64_t)n};
+        cuuint64_t strides[4] = {(cuuint64_t)channels * 2, (cuuint64_t)OW * channels * 2, plane, 4 * plane};
+        cuuint32_t box[5] = {64, (cuuint32_t)OW, (cuuint32_t)OH, 1, (cuuint32_t)per_tile};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = fn(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("conv2d_nhwc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return I2V_ERR_INVALID;
+        }
+    } else {
         const int per_tile = kBM / rows;
         cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n};
         cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)width * channels * 2,
@@ -869,11 +903,27 @@ extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float
     }
     I2V_TRY(make_map(&map_w, w, 0, out_channels, K, ldw, 128));
     const int M = n * rows;
-    ConvGeom cg{chunks, kernel, pad, rows};
+    ConvGeom cg{chunks, kernel, pad, rows, split ? 1 : 0};
     dim3 grid(1u, (unsigned)ceil_div(M, kBM));
     auto kern = linear_tcgen05_kernel<0, 128, true>;
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<128>::kSmemBytes));
     kern<<<grid, kThreads, Tile<128>::kSmemBytes, stream>>>(map_x, map_w, bias, y, M, out_channels, K, ldy,
                                                            out_dtype == I2V_DT_BF16, relu, cg, DropMask{});
     return check_launch("linear_tcgen05_kernel<conv>");
+}
+
+extern "C" int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
+                                       int channels, int out_channels, int kernel, int stride, int pad, long long ldw,
+                                       long long ldy, int out_dtype, int relu, cudaStream_t stream) {
+    return conv2d_nhwc_impl(x, w, bias, y, n, height, width, channels, out_channels, kernel, stride, pad, ldw, ldy, out_dtype,
+                            relu, false, stream);
+}
+
+// The same stride-2 layer on a parity-split activation x [N, 2, 2, H/2, W/2, C] (what i2v_pair_conv1_split_bf16 writes);
+// `height` and `width` are those of the whole map.  y as above.
+extern "C" int i2v_conv2d_nhwc_split_forward(const void* x, const void* w, const float* bias, void* y, int n, int height,
+                                             int width, int channels, int out_channels, int kernel, int pad, long long ldw,
+                                             long long ldy, int out_dtype, int relu, cudaStream_t stream) {
+    return conv2d_nhwc_impl(x, w, bias, y, n, height, width, channels, out_channels, kernel, 2, pad, ldw, ldy, out_dtype, relu,
+                            true, stream);
 }

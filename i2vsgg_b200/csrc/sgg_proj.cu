@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
 //     conv(pair)[pos][oc] = S[subject][pos][oc] + S[object][pos][C + oc] + bias[oc]
 // with S[obj][pos][0..C) / [C..2C) the single-channel convolutions of the object's mask with the subject / object half of
 // the kernel (one small FC launch over N objects instead of P pairs).  This kernel does the add, the ReLU and the bf16
-// rounding, 8 output channels (16 bytes) per thread; out is NHWC [P, positions, C].
+// rounding, 8 output channels (16 bytes) per thread; out is NHWC [P, positions, C], or -- `ow` > 0, positions = oh x ow, both
+// even -- the parity-split layout [P, 2, 2, oh/2, ow/2, C] (plane (y & 1, x & 1), position (y >> 1, x >> 1)) in which a
+// stride-2 convolution reads dense boxes (i2v_conv2d_nhwc_split_forward).
 __global__ void __launch_bounds__(256) pair_conv1_kernel(const float* __restrict__ S, const int64_t* __restrict__ ixs,
                                                          const int64_t* __restrict__ ixo, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int64_t total8, int num_obj,
-                                                         int positions, int C, int relu) {
+                                                         int positions, int C, int relu, int ow) {
     const int chunks = C / 8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
         const int ch = (int)(i % chunks);
@@ -175,7 +177,13 @@ __global__ void __launch_bounds__(256) pair_conv1_kernel(const float* __restrict
         __nv_bfloat16 o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(relu ? fmaxf(v[j], 0.f) : v[j]);
-        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<uint4*>(o);
+        int64_t dst = i;
+        if (ow > 0) {
+            const int y = pos / ow, x = pos - y * ow;
+            const int plane = ((y & 1) << 1) | (x & 1), sub = (y >> 1) * (ow >> 1) + (x >> 1);
+            dst = ((p * 4 + plane) * (positions >> 2) + sub) * chunks + ch;
+        }
+        *reinterpret_cast<uint4*>(out + dst * 8) = *reinterpret_cast<uint4*>(o);
     }
 }
 
@@ -307,8 +315,8 @@ extern "C" int i2v_gather_rows_bf16(const void* src, const int64_t* idx, void* o
     return check_launch("gather_rows_kernel");
 }
 
-extern "C" int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
-                                   int num_obj, int num_pairs, int positions, int channels, int relu, cudaStream_t stream) {
+static int pair_conv1_impl(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
+                           int num_obj, int num_pairs, int positions, int channels, int relu, int ow, cudaStream_t stream) {
     I2V_REQUIRE(num_obj >= 0 && num_pairs >= 0 && positions >= 1 && channels >= 8 && channels % 8 == 0,
                 "pair_conv1: bad shape (channels must be a multiple of 8)");
     if (num_pairs == 0) return I2V_OK;
@@ -317,6 +325,19 @@ extern "C" int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, co
     int64_t total8 = (int64_t)num_pairs * positions * (channels / 8);
     pair_conv1_kernel<<<grid_for(total8, 256, 16), 256, 0, stream>>>(obj_maps, ixs, ixo, bias,
                                                                      static_cast<__nv_bfloat16*>(out), total8, num_obj,
-                                                                     positions, channels, relu);
+                                                                     positions, channels, relu, ow);
     return check_launch("pair_conv1_kernel");
+}
+
+extern "C" int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
+                                   int num_obj, int num_pairs, int positions, int channels, int relu, cudaStream_t stream) {
+    return pair_conv1_impl(obj_maps, ixs, ixo, bias, out, num_obj, num_pairs, positions, channels, relu, 0, stream);
+}
+
+// the same rows in the parity-split layout [P, 2, 2, oh/2, ow/2, C] (see pair_conv1_kernel)
+extern "C" int i2v_pair_conv1_split_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias,
+                                         void* out, int num_obj, int num_pairs, int oh, int ow, int channels, int relu,
+                                         cudaStream_t stream) {
+    I2V_REQUIRE(oh >= 2 && ow >= 2 && oh % 2 == 0 && ow % 2 == 0, "pair_conv1_split: the map must have even sides");
+    return pair_conv1_impl(obj_maps, ixs, ixo, bias, out, num_obj, num_pairs, oh * ow, channels, relu, ow, stream);
 }

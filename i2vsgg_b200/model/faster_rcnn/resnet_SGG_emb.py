@@ -208,11 +208,17 @@ class vrd(nn.Module):
                 lo = self.conv_lo[1].forward_tf32(lo, "nhwc")
                 lo = self.conv_lo[2].forward_tf32(lo, "nhwc").reshape(n_pair, 64)
             elif obj_masks is not None:
-                lo = self.conv_lo[0].forward_pairs(_dev(obj_masks, dev).reshape(n_obj, 32, 32).contiguous(), ix1, ix2)
+                # the first layer writes parity planes when the second (stride 2) can read them as dense TMA boxes
+                c0 = self.conv_lo[0].conv
+                oh0 = (32 + 2 * c0.padding[0] - c0.kernel_size[0]) // c0.stride[0] + 1
+                split = self.conv_lo[1].takes_split(oh0, oh0, c0.out_channels)
+                lo = self.conv_lo[0].forward_pairs(_dev(obj_masks, dev).reshape(n_obj, 32, 32).contiguous(), ix1, ix2,
+                                                   split=split)
+                lo = self.conv_lo[1](lo, "nhwc_split" if split else "nhwc")
+                lo = self.conv_lo[2](lo, "nhwc").reshape(n_pair, 64)
             else:
                 sp = _dev(SpatialFea, dev).reshape(n_pair, 2, 32, 32).contiguous()
                 lo = self.conv_lo[0](sp, "nchw")
-            if not tf32:
                 lo = self.conv_lo[1](lo, "nhwc")
                 lo = self.conv_lo[2](lo, "nhwc").reshape(n_pair, 64)
             self.fc_lov(lo, out=fusion[:, col:col + 256])

@@ -106,10 +106,17 @@ class Conv2d(nn.Module):
         self._w_taps = taps.view(o, kh * kw * cp)
         return self
 
-    def forward_pairs(self, obj_x, ixs, ixo):
+    def takes_split(self, h, w, c):
+        """Whether `forward(x, 'nhwc_split')` applies to an [h, w, c] map: the stride-2 implicit GEMM on parity planes."""
+        kh, st, pd = self.conv.kernel_size[0], self.conv.stride[0], self.conv.padding[0]
+        return (st == 2 and kh % 2 == 1 and pd == (kh - 1) // 2 and h % 2 == 0 and w % 2 == 0 and c % 8 == 0
+                and 128 % ((h // 2) * (w // 2)) == 0 and self.conv.out_channels <= 128 and c == self.conv.in_channels)
+
+    def forward_pairs(self, obj_x, ixs, ixo, split: bool = False):
         """This layer applied to P two-channel inputs whose channels are `obj_x[ixs[p]]` and `obj_x[ixo[p]]`
         (obj_x [N,H,W]): the convolution is linear in its input channels, so each OBJECT map is convolved once with
-        either half of the kernel and a pair is the sum of two rows plus the bias.  -> NHWC bf16 [P,OH,OW,out]."""
+        either half of the kernel and a pair is the sum of two rows plus the bias.  -> NHWC bf16 [P,OH,OW,out], or with
+        `split` the parity-split layout [P,2,2,OH/2,OW/2,out] that the next layer's `forward(x, 'nhwc_split')` reads."""
         self._fresh()
         o, kh = self.conv.out_channels, self.conv.kernel_size[0]
         if self.conv.in_channels != 2:
@@ -126,6 +133,9 @@ class Conv2d(nn.Module):
         patches, (_, oh, ow) = ops.im2col_bf16(obj_x.reshape(n, 1, h, wd).contiguous(), kh, self.conv.stride[0],
                                                self.conv.padding[0], "nchw", ld=self._kp_pair)
         maps = ops.linear(patches, self._w_pair, None, relu=False, out_dtype=torch.float32)       # [N*OH*OW, 2*out]
+        if split:
+            return ops.pair_conv1_bf16(maps.view(n, oh * ow, 2 * o), ixs, ixo, self._b, relu=self.relu is not None,
+                                       split_hw=(oh, ow))
         y = ops.pair_conv1_bf16(maps.view(n, oh * ow, 2 * o), ixs, ixo, self._b, relu=self.relu is not None)
         return y.view(ixs.numel(), oh, ow, o)
 
@@ -158,6 +168,8 @@ class Conv2d(nn.Module):
         self._fresh()
         kh = self.conv.kernel_size[0]
         st, pd = self.conv.stride[0], self.conv.padding[0]
+        if layout == "nhwc_split":      # [N,2,2,H/2,W/2,C] parity planes (see `takes_split`)
+            return ops.conv2d_nhwc_split(x, self._w_taps, self._b, kh, pd, relu=self.relu is not None)
         if layout == "nhwc" and x.dtype == torch.bfloat16 and x.is_contiguous() and st > 1:
             oh, ow = (x.size(1) + 2 * pd - kh) // st + 1, (x.size(2) + 2 * pd - kh) // st + 1
             if 128 % (oh * ow) == 0 and x.size(3) % 8 == 0 and self.conv.out_channels <= 128:

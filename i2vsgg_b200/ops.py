@@ -428,6 +428,22 @@ def rel_scores(x, prd, softmax: bool = True):
     return out
 
 
+def conv2d_nhwc_split(x, weight_taps, bias, kernel: int, pad: int, relu: bool = True, out_dtype=torch.bfloat16):
+    """`conv2d_nhwc` with stride 2 on a parity-split activation x [N, 2, 2, H/2, W/2, C] bf16 (plane (y & 1, x & 1),
+    position (y >> 1, x >> 1)) -> [N, H/2, W/2, O]; same bits as the strided call on the unsplit map."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 6 or not x.is_contiguous() or x.size(1) != 2 or x.size(2) != 2:
+        raise _lib.I2VError("conv2d_nhwc_split: expected a contiguous [N,2,2,H/2,W/2,C] bf16 CUDA tensor")
+    n, _, _, h2, w2, c = x.shape
+    o = weight_taps.size(0)
+    out = torch.empty((n, h2, w2, o), dtype=out_dtype, device=x.device)
+    b = None if bias is None else _f32(bias, "bias")
+    with torch.cuda.device(x.device):
+        check(load().i2v_conv2d_nhwc_split_forward(_p(x), _p(weight_taps), _p(b), _p(out), n, 2 * h2, 2 * w2, c, o, kernel, pad,
+                                                   weight_taps.stride(0), o, _TORCH_DT[out_dtype], int(bool(relu)), _stream()),
+              "i2v_conv2d_nhwc_split_forward")
+    return out
+
+
 def im2col_bf16(x, kernel: int, stride: int, pad: int, layout: str, ld: int | None = None, out_dtype=torch.bfloat16):
     """Patches of a square-kernel convolution as bf16 (or fp32) rows [(n, oy, ox), (ky, kx, c)] (pitch `ld`, zero padded).
     x is [N,C,H,W] (`layout='nchw'`) or [N,H,W,C] (`layout='nhwc'`), fp32 or bf16, contiguous."""
@@ -508,16 +524,26 @@ def greedy_association(records, counts, frame_numbers=None, source_frame=None, m
     return rel_id, order, info, score, num
 
 
-def pair_conv1_bf16(obj_maps, ixs, ixo, bias, relu: bool = True):
+def pair_conv1_bf16(obj_maps, ixs, ixo, bias, relu: bool = True, split_hw=None):
     """obj_maps [N, positions, 2C] fp32 (per-object single-channel convolutions, subject half then object half) ->
-    relu(obj_maps[ixs][..., :C] + obj_maps[ixo][..., C:] + bias) as NHWC bf16 [P, positions, C]."""
+    relu(obj_maps[ixs][..., :C] + obj_maps[ixo][..., C:] + bias) as NHWC bf16 [P, positions, C]; with `split_hw` = (oh, ow)
+    (positions = oh*ow, both even) in the parity-split layout [P, 2, 2, oh/2, ow/2, C] of `conv2d_nhwc_split`."""
     obj_maps = _f32(obj_maps, "obj_maps")
     N, positions, c2 = obj_maps.shape
     C = c2 // 2
     ixs, ixo = ixs.long().contiguous(), ixo.long().contiguous()
     P = ixs.numel()
-    out = torch.empty((P, positions, C), dtype=torch.bfloat16, device=obj_maps.device)
     b = None if bias is None else _f32(bias, "bias")
+    if split_hw is not None:
+        oh, ow = split_hw
+        if oh * ow != positions:
+            raise _lib.I2VError("pair_conv1_bf16: split_hw does not match the number of positions")
+        out = torch.empty((P, 2, 2, oh // 2, ow // 2, C), dtype=torch.bfloat16, device=obj_maps.device)
+        with torch.cuda.device(obj_maps.device):
+            check(load().i2v_pair_conv1_split_bf16(_p(obj_maps), _p(ixs), _p(ixo), _p(b), _p(out), N, P, oh, ow, C,
+                                                   int(bool(relu)), _stream()), "i2v_pair_conv1_split_bf16")
+        return out
+    out = torch.empty((P, positions, C), dtype=torch.bfloat16, device=obj_maps.device)
     with torch.cuda.device(obj_maps.device):
         check(load().i2v_pair_conv1_bf16(_p(obj_maps), _p(ixs), _p(ixo), _p(b), _p(out), N, P, positions, C,
                                          int(bool(relu)), _stream()), "i2v_pair_conv1_bf16")

@@ -280,12 +280,24 @@ int i2v_pair_rows_bf16(const float* obj, const int64_t* ixs, const int64_t* ixo,
 int i2v_conv2d_nhwc_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
                             int channels, int out_channels, int kernel, int stride, int pad, long long ldw,
                             long long ldy, int out_dtype, int relu, cudaStream_t stream);
+/* The same layer for stride 2 on a PARITY-SPLIT activation: x [N, 2, 2, H/2, W/2, C] bf16, plane (y & 1, x & 1) holding
+ * position (y >> 1, x >> 1) of the H x W map (`height`, `width` are the whole map's; both even, pad = (kernel - 1) / 2).
+ * The samples of a filter tap are then a dense box of one plane, which the TMA fetches at full rate; the strided box of
+ * i2v_conv2d_nhwc_forward makes it walk the skipped positions too.  Same results bit for bit.  The relation head's first
+ * conv layer writes this layout directly (i2v_pair_conv1_split_bf16). */
+int i2v_conv2d_nhwc_split_forward(const void* x, const void* w, const float* bias, void* y, int n, int height, int width,
+                                  int channels, int out_channels, int kernel, int pad, long long ldw, long long ldy,
+                                  int out_dtype, int relu, cudaStream_t stream);
 /* First layer of conv_lo for ordered pairs (resnet_SGG_emb.py:107,182): a pair's two mask channels are the masks of
  * its subject and object, so conv(pair) = S[subject][.., 0:C] + S[object][.., C:2C] + bias, where obj_maps
  * [N, positions, 2C] fp32 holds the two single-channel convolutions of every OBJECT mask (one small FC launch).
  * out [P, positions, C] bf16 (NHWC), ReLU when `relu`. */
 int i2v_pair_conv1_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
                         int num_obj, int num_pairs, int positions, int channels, int relu, cudaStream_t stream);
+/* The same rows in the parity-split layout [P, 2, 2, oh/2, ow/2, C] (positions = oh x ow, both even) that
+ * i2v_conv2d_nhwc_split_forward reads. */
+int i2v_pair_conv1_split_bf16(const float* obj_maps, const int64_t* ixs, const int64_t* ixo, const float* bias, void* out,
+                              int num_obj, int num_pairs, int oh, int ow, int channels, int relu, cudaStream_t stream);
 /* out[p] = src[idx[p]] for bf16 rows (cols % 8 == 0; pitches in elements, multiples of 8).  Used to fan the rows computed
  * once per UNORDERED pair back out to both orderings: the union boxes of (i,j) and (j,i) are the same box
  * (resnet_SGG_emb.py:240-244 is symmetric), so their pooled / fc6 / fc7 / fc8 rows are identical. */

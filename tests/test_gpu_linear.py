@@ -173,6 +173,41 @@ def test_conv2d_nhwc_implicit_gemm_matches_torch(ops, c, o, h, k, stride, pad):
     assert float((y.permute(0, 3, 1, 2).double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
 
 
+@pytest.mark.parametrize("c,o,h,k", [(96, 128, 16, 5), (64, 32, 16, 3), (8, 128, 8, 3), (72, 100, 4, 7)])
+def test_conv2d_on_parity_planes_equals_the_strided_call(ops, c, o, h, k):
+    """Stride-2 convolution on the parity-split activation ([N,2,2,H/2,W/2,C], dense 5-D TMA boxes) against the strided
+    4-D map on the plain NHWC tensor: the same k-blocks in the same order, so the same bits; and against F.conv2d."""
+    g = torch.Generator(device="cuda").manual_seed(c * 3 + o)
+    n, pad = 37, (k - 1) // 2
+    x = torch.randn((n, h, h, c), device="cuda", generator=g).bfloat16()
+    w = (torch.randn((o, c, k, k), device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn((o,), device="cuda", generator=g)
+    cp = (c + 63) // 64 * 64
+    taps = torch.zeros((o, k * k, cp), device="cuda", dtype=torch.bfloat16)
+    taps[:, :, :c] = w.permute(0, 2, 3, 1).reshape(o, k * k, c)
+    xs = x.view(n, h // 2, 2, h // 2, 2, c).permute(0, 2, 4, 1, 3, 5).contiguous()     # [n, py, px, y', x', c]
+    got = ops.conv2d_nhwc_split(xs, taps.view(o, -1), b, k, pad, relu=True, out_dtype=torch.float32)
+    want = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=pad))
+    assert got.shape == (n, h // 2, h // 2, o)
+    assert float((got.permute(0, 3, 1, 2).double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    if 128 % ((h // 2) ** 2) == 0:
+        plain = ops.conv2d_nhwc(x, taps.view(o, -1), b, k, 2, pad, relu=True, out_dtype=torch.float32)
+        assert torch.equal(got, plain)
+
+
+def test_pair_conv1_parity_planes_are_a_permutation_of_the_nhwc_rows(ops):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, oh, ow, c = 9, 16, 16, 96
+    maps = torch.randn((n, oh * ow, 2 * c), device="cuda", generator=g)
+    ixs = torch.randint(0, n, (50,), device="cuda", generator=g)
+    ixo = torch.randint(0, n, (50,), device="cuda", generator=g)
+    bias = torch.randn((c,), device="cuda", generator=g)
+    plain = ops.pair_conv1_bf16(maps, ixs, ixo, bias).view(50, oh, ow, c)
+    split = ops.pair_conv1_bf16(maps, ixs, ixo, bias, split_hw=(oh, ow))
+    assert split.shape == (50, 2, 2, oh // 2, ow // 2, c)
+    assert torch.equal(split, plain.view(50, oh // 2, 2, ow // 2, 2, c).permute(0, 2, 4, 1, 3, 5).contiguous())
+
+
 @pytest.mark.parametrize("shape", [(1, 1024, 38, 63), (2, 64, 63, 38)])   # config-3 frame; portrait map (pitch 41)
 def test_roi_pool_rows_bf16_planes_equal_fp32_planes(ops, shape):
     """The bf16-plane kernel (two channels per word, max.bf16x2) against the fp32-plane kernel rounded at the end and the
