@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 // from both shared memories and either half of B from its owner, and each CTA ends up with its own 128 accumulator rows
 // in its own tensor memory.  Per k-block a CTA moves 32 KB instead of 48 KB through L2 and shared memory for the same
 // flops, which is what the single-CTA kernel is bound by (19 GB of tile traffic for fc6 = 14.5 TB/s at 78 % of peak).
-constexpr int kPairBBytes = 128 * kRowBytes;                       // this CTA's half of the W tile
-constexpr int kPairStageBytes = kABytes + kPairBBytes;             // 32 KB
-constexpr size_t pair_smem_bytes(int stages) { return (size_t)stages * kPairStageBytes + 1024 + 256; }
+constexpr size_t pair_smem_bytes(int stages, int bn = 256) {       // a stage: 128 x rows + bn / 2 W rows (32 KB at bn = 256)
+    return (size_t)stages * (kABytes + (bn / 2) * kRowBytes) + 1024 + 256;
+}
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                        // shared::cluster address of the same offset in CTA 0
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -335,6 +335,23 @@ __device__ __forceinline__ void tma_load_2d_pair(void* sdst, const CUtensorMap* 
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(leader_bar) & kPeerMask)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(void* sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                 uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+        "%5}], [%6];" ::"r"(smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(leader_bar) & kPeerMask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                                 uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+        "%5, %6}], [%7];" ::"r"(smem_u32(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+        "r"(smem_u32(leader_bar) & kPeerMask)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on `bar` in both CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
@@ -342,16 +359,19 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives o
                  : "memory");
 }
 
-template <int KIND, int kPairStages>
+// BN = 128 (one tile column of at most 128 outputs: conv_lo's layers) halves the W half to 64 rows; CONV reads x through
+// the implicit-GEMM maps of linear_tcgen05_kernel.
+template <int KIND, int kPairStages, int BN = 256, bool CONV = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     linear_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                const float* __restrict__ bias, void* __restrict__ y, int M, int N, int K, long long ldy,
-                               int y_bf16, int relu, const DropMask dm) {
+                               int y_bf16, int relu, const DropMask dm, ConvGeom cg) {
     constexpr int ELEMS = (KIND == 0) ? 64 : 32;
     constexpr uint32_t FMT = (KIND == 0) ? 1u : 2u;
-    // D = fp32, A/B format, K-major, N = 256 (>> 3), M = 256 (>> 4)
-    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    constexpr int kTmemCols = 256;
+    // D = fp32, A/B format, K-major, N = BN (>> 3), M = 256 (>> 4)
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr int kTmemCols = BN;
+    constexpr int kPairStageBytes = kABytes + (BN / 2) * kRowBytes;    // this CTA's x rows + its half of the W tile
 
     extern __shared__ uint8_t raw_smem[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
@@ -365,7 +385,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const bool leader = rank == 0;
     const int m0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * 128;   // this CTA's 128 rows of x
-    const int n0 = blockIdx.y * 256;                                 // the pair's 256 columns
+    const int n0 = blockIdx.y * BN;                                  // the pair's BN columns
     const int kblocks = (K + ELEMS - 1) / ELEMS;
 
     if (warp == 0 && lane == 0) {
@@ -403,8 +423,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 // remote arrive per k-block from the peer would cost a cluster-scope release fence (~1500 cycles here).
                 if (leader) mbar_expect_tx(full + s, 2 * kPairStageBytes);
                 uint8_t* a = smem + (size_t)s * kPairStageBytes;
-                tma_load_2d_pair(a, &map_x, kb * ELEMS, m0, full + s);
-                tma_load_2d_pair(a + kABytes, &map_w, kb * ELEMS, n0 + (int)rank * 128, full + s);
+                if (CONV) {
+                    const int tap = kb / cg.chunks, chunk = kb - tap * cg.chunks;
+                    const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
+                    const int dx = kx - cg.pad, dy = ky - cg.pad;
+                    if (cg.split)
+                        tma_load_5d_pair(a, &map_x, chunk * ELEMS, dx >> 1, dy >> 1, ((dy & 1) << 1) | (dx & 1),
+                                         m0 / cg.rows_per_image, full + s);
+                    else
+                        tma_load_4d_pair(a, &map_x, chunk * ELEMS, dx, dy, m0 / cg.rows_per_image, full + s);
+                } else {
+                    tma_load_2d_pair(a, &map_x, kb * ELEMS, m0, full + s);
+                }
+                tma_load_2d_pair(a + kABytes, &map_w, kb * ELEMS, n0 + (int)rank * (BN / 2), full + s);
             }
         }
     } else if (warp == 1) {
@@ -442,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum, 0);
         tc_fence_after();
-        epilogue_rows<256>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu, dm);
+        epilogue_rows<BN>(tmem_base, q, lane, row, n0, bias, y, M, N, ldy, y_bf16, relu, dm);
     }
     tc_fence_before();
     __syncthreads();
@@ -731,11 +762,11 @@ static int linear_impl(const void* x, const void* w, const float* bias, void* y,
         if (kind == 0) {
             auto kern = linear_tcgen05_pair_kernel<0, kPairStages>;
             I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
-            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm);
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm, ConvGeom{});
         } else {
             auto kern = linear_tcgen05_pair_kernel<1, kPairStages>;
             I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(kPairStages)));
-            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm);
+            kern<<<grid2, kThreads, pair_smem_bytes(kPairStages), stream>>>(map_x, map_w, bias, y, M, N, K, ldy, yb2, relu, dm, ConvGeom{});
         }
         return check_launch("linear_tcgen05_pair_kernel");
     }
@@ -904,6 +935,23 @@ static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, voi
     I2V_TRY(make_map(&map_w, w, 0, out_channels, K, ldw, 128));
     const int M = n * rows;
     ConvGeom cg{chunks, kernel, pad, rows, split ? 1 : 0};
+    static const bool pair_off = getenv("I2V_LINEAR_1CTA") != nullptr;
+    if (M > kBM && !pair_off) {
+        // CTA pairs: a 256-row tile per pair, every CTA loading its own 128 rows of patches and 64 of the 128 W rows.  With a
+        // 128-wide tile an SM's shared memory moves 64 KB per k-block (32 KB written by the TMA, 32 KB read by the MMAs) in
+        // the 256 cycles the MMAs take -- twice its 128 B/clk -- and the pair brings that to 48 KB (0.93 -> 0.86 ms for
+        // conv_lo's second layer); four stages, so that two CTAs share an SM as in the 1-CTA kernel
+        alignas(64) CUtensorMap map_w2;
+        I2V_TRY(make_map(&map_w2, w, 0, out_channels, K, ldw, 64));
+        constexpr int kConvStages = 4;
+        auto kern2 = linear_tcgen05_pair_kernel<0, kConvStages, 128, true>;
+        I2V_CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)pair_smem_bytes(kConvStages, 128)));
+        dim3 grid2(2u * (unsigned)ceil_div(M, 256), 1u);
+        kern2<<<grid2, kThreads, pair_smem_bytes(kConvStages, 128), stream>>>(map_x, map_w2, bias, y, M, out_channels, K, ldy,
+                                                                             out_dtype == I2V_DT_BF16, relu, DropMask{}, cg);
+        return check_launch("linear_tcgen05_pair_kernel<conv>");
+    }
     dim3 grid(1u, (unsigned)ceil_div(M, kBM));
     auto kern = linear_tcgen05_kernel<0, 128, true>;
     I2V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<128>::kSmemBytes));
