@@ -150,40 +150,56 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
 // rounding, 8 output channels (16 bytes) per thread; out is NHWC [P, positions, C], or -- `ow` > 0, positions = oh x ow, both
 // even -- the parity-split layout [P, 2, 2, oh/2, ow/2, C] (plane (y & 1, x & 1), position (y >> 1, x >> 1)) in which a
 // stride-2 convolution reads dense boxes (i2v_conv2d_nhwc_split_forward).
+constexpr int kPairRun = 8;     // consecutive pairs per thread: the pair list is subject-major, so a run mostly shares its subject
 __global__ void __launch_bounds__(256) pair_conv1_kernel(const float* __restrict__ S, const int64_t* __restrict__ ixs,
                                                          const int64_t* __restrict__ ixo, const float* __restrict__ bias,
-                                                         __nv_bfloat16* __restrict__ out, int64_t total8, int num_obj,
+                                                         __nv_bfloat16* __restrict__ out, int64_t num_pairs, int num_obj,
                                                          int positions, int C, int relu, int ow) {
     const int chunks = C / 8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % chunks);
-        const int64_t pp = i / chunks;
-        const int pos = (int)(pp % positions);
-        const int64_t p = pp / positions;
-        const int64_t a = ixs[p], b = ixo[p];
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = bias ? __ldg(bias + ch * 8 + j) : 0.f;
-        if (a >= 0 && a < num_obj) {
-            const float4* s = reinterpret_cast<const float4*>(S + ((size_t)a * positions + pos) * 2 * C + ch * 8);
-            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
-            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-        }
-        if (b >= 0 && b < num_obj) {
-            const float4* s = reinterpret_cast<const float4*>(S + ((size_t)b * positions + pos) * 2 * C + C + ch * 8);
-            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
-            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-        }
-        __nv_bfloat16 o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(relu ? fmaxf(v[j], 0.f) : v[j]);
-        int64_t dst = i;
+    const int64_t per_pair = (int64_t)positions * chunks;
+    const int64_t runs = (num_pairs + kPairRun - 1) / kPairRun;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < runs * per_pair; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t run = i / per_pair;
+        const int e = (int)(i - run * per_pair);           // (position, 8-channel chunk) of this thread
+        const int pos = e / chunks, ch = e - pos * chunks;
+        int64_t dst_in_pair = e;
         if (ow > 0) {
             const int y = pos / ow, x = pos - y * ow;
             const int plane = ((y & 1) << 1) | (x & 1), sub = (y >> 1) * (ow >> 1) + (x >> 1);
-            dst = ((p * 4 + plane) * (positions >> 2) + sub) * chunks + ch;
+            dst_in_pair = ((int64_t)plane * (positions >> 2) + sub) * chunks + ch;
         }
-        *reinterpret_cast<uint4*>(out + dst * 8) = *reinterpret_cast<uint4*>(o);
+        float base[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) base[j] = bias ? __ldg(bias + ch * 8 + j) : 0.f;
+        float sv[8];                                        // bias + the subject's half, kept while the subject stays
+        int64_t cur = -2;
+        const int64_t p_end = min(num_pairs, (run + 1) * kPairRun);
+        for (int64_t p = run * kPairRun; p < p_end; ++p) {
+            const int64_t a = ixs[p], b = ixo[p];
+            if (a != cur) {
+                cur = a;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sv[j] = base[j];
+                if (a >= 0 && a < num_obj) {
+                    const float4* s = reinterpret_cast<const float4*>(S + ((size_t)a * positions + pos) * 2 * C + ch * 8);
+                    const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+                    sv[0] += s0.x; sv[1] += s0.y; sv[2] += s0.z; sv[3] += s0.w;
+                    sv[4] += s1.x; sv[5] += s1.y; sv[6] += s1.z; sv[7] += s1.w;
+                }
+            }
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sv[j];
+            if (b >= 0 && b < num_obj) {
+                const float4* s = reinterpret_cast<const float4*>(S + ((size_t)b * positions + pos) * 2 * C + C + ch * 8);
+                const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+                v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+            }
+            __nv_bfloat16 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(relu ? fmaxf(v[j], 0.f) : v[j]);
+            *reinterpret_cast<uint4*>(out + (p * per_pair + dst_in_pair) * 8) = *reinterpret_cast<uint4*>(o);
+        }
     }
 }
 
@@ -322,10 +338,10 @@ static int pair_conv1_impl(const float* obj_maps, const int64_t* ixs, const int6
     if (num_pairs == 0) return I2V_OK;
     I2V_REQUIRE(obj_maps && ixs && ixo && out, "pair_conv1: null pointer");
     I2V_REQUIRE(((uintptr_t)obj_maps & 15) == 0 && ((uintptr_t)out & 15) == 0, "pair_conv1: 16-byte aligned buffers needed");
-    int64_t total8 = (int64_t)num_pairs * positions * (channels / 8);
-    pair_conv1_kernel<<<grid_for(total8, 256, 16), 256, 0, stream>>>(obj_maps, ixs, ixo, bias,
-                                                                     static_cast<__nv_bfloat16*>(out), total8, num_obj,
-                                                                     positions, channels, relu, ow);
+    const int64_t threads = (int64_t)ceil_div(num_pairs, kPairRun) * positions * (channels / 8);
+    pair_conv1_kernel<<<grid_for(threads, 256, 16), 256, 0, stream>>>(obj_maps, ixs, ixo, bias,
+                                                                      static_cast<__nv_bfloat16*>(out), num_pairs, num_obj,
+                                                                      positions, channels, relu, ow);
     return check_launch("pair_conv1_kernel");
 }
 
