@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libi2vsgg_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
-IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, IMPL_ROWS, IMPL_PHASE, IMPL_BAND, IMPL_SLAB, IMPL_EVEN = 0, 1, 2, 3, 4, 5, 6, 7
+IMPL_AUTO, IMPL_GATHER, IMPL_PLANE, IMPL_ROWS, IMPL_PHASE, IMPL_BAND, IMPL_SLAB, IMPL_EVEN, IMPL_CHAN = 0, 1, 2, 3, 4, 5, 6, 7, 8
 ARGMAX_FLAT, ARGMAX_PLANE = 0, 1
 DT_F32, DT_BF16, DT_TF32 = 0, 1, 2
 

@@ -752,6 +752,9 @@ bool fwd_slab_ok(const float* features, const float* out, int batch, int C, int 
 int launch_fwd_slab(const float* feat, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts, float* out,
                     int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 // roi_align_fwd_even.cu: the forward on planes re-pitched to an even row pitch (conflict free by construction)
+bool fwd_chan_ok(const float* features, const float* out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
+int launch_fwd_chan(const float* feat, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts, float* out,
+                    int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
 bool fwd_even_ok(const float* features, const float* out, int batch, int C, int H, int W, int PH, int PW, int pool_mode);
 int launch_fwd_even(const float* feat, const LatticeRoi* tab, void* tab_space, const int* order, const int* starts, float* out,
                     int batch, int C, int H, int W, int num_rois, int pool_mode, cudaStream_t stream);
@@ -896,7 +899,7 @@ static int roi_align_check(const char* who, const void* a, const void* b, const 
                            int& GH, int& GW) {
     I2V_REQUIRE(batch >= 0 && channels >= 0 && num_rois >= 0, "%s: negative size", who);
     I2V_REQUIRE(pool_mode >= I2V_POOL_NONE && pool_mode <= I2V_POOL_MAX, "%s: bad pool_mode %d", who, pool_mode);
-    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_EVEN, "%s: bad impl %d", who, impl);
+    I2V_REQUIRE(impl >= I2V_IMPL_AUTO && impl <= I2V_IMPL_CHAN, "%s: bad impl %d", who, impl);
     GH = pooled_h + (pool_mode != I2V_POOL_NONE);
     GW = pooled_w + (pool_mode != I2V_POOL_NONE);
     I2V_REQUIRE(pooled_h >= 1 && pooled_w >= 1 && GH >= 2 && GW >= 2 && GH <= kMaxLattice && GW <= kMaxLattice,
@@ -947,6 +950,17 @@ extern "C" int i2v_roi_align_forward(const float* features, const float* rois, f
         I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, true, w));
         I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
         return launch_fwd_even(features, w.tab, w.ptab, w.order, w.starts, out, batch, channels, height, width, num_rois,
+                               pool_mode, stream);
+    }
+    if (impl == I2V_IMPL_CHAN) {
+        if (!fwd_chan_ok(features, out, batch, channels, height, width, pooled_h, pooled_w, pool_mode)) {
+            set_error("roi_align_forward: the lane-per-channel kernel needs a 7x7 output, pool none/avg, C %% 32 == 0, W <= 64 and "
+                      "half the rows of 32 planes in shared memory");
+            return I2V_ERR_UNSUPPORTED;
+        }
+        I2V_TRY(carve_checked("roi_align_forward", workspace, workspace_bytes, batch, num_rois, true, w));
+        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        return launch_fwd_chan(features, w.tab, w.ptab, w.order, w.starts, out, batch, channels, height, width, num_rois,
                                pool_mode, stream);
     }
     if (impl >= I2V_IMPL_PLANE && impl != I2V_IMPL_SLAB && !can_plane) {
@@ -1003,8 +1017,8 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
     bool can_phase = num_rois > 0 && bwd_phase_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
     bool can_band = zero_first && num_rois > 0 &&
                     bwd_band_ok(grad_out, batch, channels, height, width, pooled_h, pooled_w, pool_mode);
-    if (impl == I2V_IMPL_SLAB || impl == I2V_IMPL_EVEN) {
-        set_error("roi_align_backward: I2V_IMPL_SLAB / I2V_IMPL_EVEN are forward kernels");
+    if (impl == I2V_IMPL_SLAB || impl == I2V_IMPL_EVEN || impl == I2V_IMPL_CHAN) {
+        set_error("roi_align_backward: I2V_IMPL_SLAB / I2V_IMPL_EVEN / I2V_IMPL_CHAN are forward kernels");
         return I2V_ERR_UNSUPPORTED;
     }
     if ((impl == I2V_IMPL_PLANE && !can_plane) || (impl == I2V_IMPL_ROWS && !can_rows) ||

@@ -10,14 +10,14 @@ import torch
 
 from . import _lib
 from ._lib import (ARGMAX_FLAT, ARGMAX_PLANE, DT_BF16, DT_F32, DT_TF32, IMPL_AUTO, IMPL_BAND, IMPL_GATHER, IMPL_PHASE, IMPL_PLANE,
-                   IMPL_EVEN, IMPL_ROWS, IMPL_SLAB,
+                   IMPL_CHAN, IMPL_EVEN, IMPL_ROWS, IMPL_SLAB,
                    POOL_AVG, POOL_MAX, POOL_NONE, check, load)
 
 _POOLS = {"none": POOL_NONE, "avg": POOL_AVG, "max": POOL_MAX, POOL_NONE: POOL_NONE, POOL_AVG: POOL_AVG,
           POOL_MAX: POOL_MAX}
-_IMPLS = {"auto": IMPL_AUTO, "gather": IMPL_GATHER, "plane": IMPL_PLANE, "rows": IMPL_ROWS, "phase": IMPL_PHASE, "band": IMPL_BAND, "slab": IMPL_SLAB, "even": IMPL_EVEN,
+_IMPLS = {"auto": IMPL_AUTO, "gather": IMPL_GATHER, "plane": IMPL_PLANE, "rows": IMPL_ROWS, "phase": IMPL_PHASE, "band": IMPL_BAND, "slab": IMPL_SLAB, "even": IMPL_EVEN, "chan": IMPL_CHAN,
           IMPL_AUTO: IMPL_AUTO, IMPL_GATHER: IMPL_GATHER, IMPL_PLANE: IMPL_PLANE, IMPL_ROWS: IMPL_ROWS, IMPL_PHASE: IMPL_PHASE,
-          IMPL_BAND: IMPL_BAND, IMPL_SLAB: IMPL_SLAB, IMPL_EVEN: IMPL_EVEN}
+          IMPL_BAND: IMPL_BAND, IMPL_SLAB: IMPL_SLAB, IMPL_EVEN: IMPL_EVEN, IMPL_CHAN: IMPL_CHAN}
 
 
 def _p(t):

@@ -88,6 +88,9 @@ void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_
 #define I2V_IMPL_EVEN 7    /* forward only: the planes re-pitched in place to an even row pitch, so that the two half-warps
                               of a load are on opposite bank parities by construction (W <= 64, H <= 40; measured 7 %
                               slower than I2V_IMPL_SLAB on config 2); I2V_ERR_UNSUPPORTED elsewhere and in the backward      */
+#define I2V_IMPL_CHAN 8    /* forward only: lanes = 32 channels, planes cell-major in two row slabs per (frame, 32 channels);
+                              a pooled row whose lattice rows lie in different slabs gets one red.add from either side
+                              (C % 32 == 0, W <= 64); I2V_ERR_UNSUPPORTED elsewhere and in the backward                     */
 
 size_t i2v_roi_align_workspace_bytes(int batch, int num_rois);
 /* features [B,C,H,W], rois [N,5] = (batch_idx,x1,y1,x2,y2) image px, out [N,C,ph,pw]; all fp32, device.

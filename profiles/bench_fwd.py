@@ -15,7 +15,7 @@ from i2vsgg_b200 import ops, synth  # noqa: E402
 
 
 def main():
-    impls = sys.argv[1:] or ["slab", "even", "plane"]
+    impls = sys.argv[1:] or ["slab", "chan", "even", "plane"]
     B, C, H, W = 32, 1024, 38, 63
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     cls, reg = synth.rpn_outputs(0, batch=B)

@@ -17,7 +17,7 @@ args = synth.VrdArgs()
 head = vrd(args, None, synth.prd_vectors(7))
 head.load_state_dict({k: torch.from_numpy(v) for k, v in synth.vrd_params(1234, args).items()})
 head = head.cuda().eval().prepare()
-F, det = 4, 64
+F, det = int(os.environ.get("GROUP", "4")), 64
 boxes, classes, conf = synth.clip_detections(5, F, det)
 b = torch.from_numpy(boxes).cuda()
 c = torch.from_numpy(np.tile(classes, (F, 1))).cuda()

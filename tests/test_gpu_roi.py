@@ -40,15 +40,20 @@ CASES = [  # (batch, channels, H, W, num_rois)
     (3, 16, 38, 63, 97),
     (2, 48, 20, 31, 50),       # runtime-width code path
 ]
+FWD_CASES = CASES + [(2, 64, 63, 38, 120)]      # portrait map (lane-per-channel kernel: 33 + 31 row slabs)
 
 
 def _fwd_combos():
     # every (case, impl, pool) the kernels take: the slab / even-pitch kernels have no max pool, the slab kernel needs
     # H * W = 2 (mod 4)
-    for case in CASES:
-        for impl in ("gather", "plane", "slab", "even", "auto"):
+    for case in FWD_CASES:
+        for impl in ("gather", "plane", "slab", "even", "chan", "auto"):
             for pool in ("none", "avg", "max"):
-                if impl in ("slab", "even") and pool == "max":
+                if impl in ("slab", "even", "chan") and pool == "max":
+                    continue
+                if impl == "chan" and case[1] % 32:
+                    continue
+                if impl == "even" and case[2] > 40:
                     continue
                 if impl == "slab" and (case[2] * case[3]) % 4 != 2:
                     continue
@@ -422,7 +427,7 @@ def test_roi_align_properties_at_config2_size(ops, orc):
     close(out[torch.from_numpy(few).cuda()], want)
 
     # the kernel bench.py times (`auto` -> the slab kernel on a 38x63 map), held to the same bar
-    for impl in ("auto", "even", "slab"):
+    for impl in ("auto", "even", "slab", "chan"):
         fast = ops.roi_align_forward(feat, rois, 7, 7, SCALE, "avg", impl)
         assert float((fast[pick] - ref).abs().max()) <= 1e-5 * scale, impl
         close(fast[torch.from_numpy(few).cuda()], want)
@@ -545,7 +550,7 @@ def test_roi_align_kernels_agree_on_random_shapes(ops):
                 assert torch.equal(out, ops.roi_align_backward(g, None, rois, (B, C, H, W), 7, 7, SCALE, pool, impl))
                 checked += 1
             fref = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, "gather")
-            for fimpl in ("auto", "even", "slab", "plane"):
+            for fimpl in ("auto", "even", "slab", "chan", "plane"):
                 try:
                     fout = ops.roi_align_forward(feat, rois, 7, 7, SCALE, pool, fimpl)
                 except I2VError:
