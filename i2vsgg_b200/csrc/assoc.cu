@@ -25,29 +25,66 @@ constexpr int kMaxK = 128;          // predictions per frame (the reference keep
 constexpr int kThreads = 128;
 constexpr int kRec = 13;            // conf, cls_s, rel, cls_o, sub box x4, obj box x4, pair idx
 
-// numpy's pairwise_sum (loops_utils.h.src) for a contiguous float64 reduction, fed with float32 confidences
-__device__ double pairwise_sum(const float* a, int n) {
+// numpy's pairwise_sum (loops_utils.h.src) for a contiguous float64 reduction, fed with float32 confidences.  numpy
+// recurses on halves (the left one rounded down to a multiple of 8) above 128 terms; the recursion is unrolled onto a small
+// explicit stack here: a recursive device function spills its caller's registers once per level and overran the default
+// 1 KB thread stack as soon as a relation was longer than 128 frames.
+__device__ __forceinline__ double pairwise_leaf(const float* a, int n) {     // n <= 128
     if (n < 8) {
         double res = 0.;
         for (int i = 0; i < n; ++i) res += (double)a[i];
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = (double)a[k];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int k = 0; k < 8; ++k) r[k] = (double)a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] += (double)a[i + k];
-        }
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += (double)a[i];
-        return res;
+        for (int k = 0; k < 8; ++k) r[k] += (double)a[i + k];
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += (double)a[i];
+    return res;
+}
+
+__device__ double pairwise_sum(const float* a, int n) {
+    if (n <= 128) return pairwise_leaf(a, n);
+    constexpr int kDepth = 24;                  // halving from 2^31 terms down to 128 needs fewer levels than this
+    int off[kDepth], len[kDepth], stage[kDepth];
+    double left[kDepth];
+    int sp = 0;
+    off[0] = 0;
+    len[0] = n;
+    stage[0] = 0;
+    double ret = 0.;
+    while (sp >= 0) {
+        if (len[sp] <= 128) {
+            ret = pairwise_leaf(a + off[sp], len[sp]);
+            --sp;
+            continue;
+        }
+        int n2 = len[sp] / 2;
+        n2 -= n2 % 8;
+        if (stage[sp] == 0) {                   // descend into the left half
+            stage[sp] = 1;
+            off[sp + 1] = off[sp];
+            len[sp + 1] = n2;
+            stage[sp + 1] = 0;
+            ++sp;
+        } else if (stage[sp] == 1) {            // left half done: keep it, descend into the right half
+            left[sp] = ret;
+            stage[sp] = 2;
+            off[sp + 1] = off[sp] + n2;
+            len[sp + 1] = len[sp] - n2;
+            stage[sp + 1] = 0;
+            ++sp;
+        } else {                                // both halves done
+            ret = left[sp] + ret;
+            --sp;
+        }
+    }
+    return ret;
 }
 
 // lib/utils.py:20-32

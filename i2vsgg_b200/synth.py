@@ -217,12 +217,14 @@ def prd_vectors(seed: int, num_relations: int = 132) -> np.ndarray:
     return np.random.default_rng(seed).standard_normal((num_relations, 300), dtype=np.float32)
 
 
-def clip_records(seed: int, frames: int = 40, tracks: int = 12, clutter: int = 8, top_k: int = 100, empty=()):
+def clip_records(seed: int, frames: int = 40, tracks: int = 12, clutter: int = 8, top_k: int = 100, empty=(),
+                 dropout: float = 0.08):
     """Per-frame triplet records of a clip as `i2v_triplet_topk` writes them: [frames, top_k, 13] fp32 =
     (conf, cls_s, rel, cls_o, sub box, obj box, pair idx) and counts [frames].  `tracks` relation tracks drift by a random
     walk (consecutive boxes overlap well above IoU 0.5), start / stop / drop out, and share a small label set so that label
     equality alone does not decide a match; `clutter` random predictions per frame never line up.  Rows are in random
-    order with unique confidences; the frame positions in `empty` have no predictions (lib/utils.py:470-518)."""
+    order with unique confidences; the frame positions in `empty` have no predictions (lib/utils.py:470-518); a track
+    misses a frame with probability `dropout` (0 gives relations as long as the track, hundreds of frames)."""
     rng = np.random.default_rng(seed)
     rec = np.zeros((frames, top_k, 13), np.float32)
     cnt = np.zeros((frames,), np.int32)
@@ -245,7 +247,7 @@ def clip_records(seed: int, frames: int = 40, tracks: int = 12, clutter: int = 8
             continue
         rows = []
         for t in range(tracks):
-            if start[t] <= f < stop[t] and rng.random() > 0.08:
+            if start[t] <= f < stop[t] and rng.random() > dropout:
                 rows.append((base[t] + rng.normal(0, 0.03), labels[t], sb[t].copy(), ob[t].copy()))
         for _ in range(clutter):
             rows.append((rng.uniform(0.01, 0.95), (int(rng.integers(1, 4)), int(rng.integers(0, 3)), int(rng.integers(1, 4))),

@@ -32,6 +32,20 @@ def test_association_equals_oracle(name):
         assert a == b
 
 
+def test_association_of_relations_hundreds_of_frames_long():
+    """Tracks that never miss a frame: relations of 300-600 frames, whose mean confidence goes through the halving levels
+    of numpy's pairwise summation (above 128 terms) -- the path that a clip of a real video takes and short tracks do not."""
+    from i2vsgg_b200 import sgg
+    from oracle import assoc
+    rec, cnt = synth.clip_records(seed=21, frames=640, tracks=14, clutter=6, dropout=0.0)
+    want = assoc.association({"vid": synth.records_to_frame_relations(rec, cnt)}).get("vid", [])
+    got = sgg.association(torch.from_numpy(rec).cuda(), torch.from_numpy(cnt).cuda())
+    assert len(got) == len(want) > 0
+    assert max(r["duration"][1] - r["duration"][0] for r in got) > 256
+    for a, b in zip(got, want):
+        assert a == b
+
+
 def test_association_frame_numbers_names_and_empty_clip():
     from i2vsgg_b200 import sgg
     from oracle import assoc
