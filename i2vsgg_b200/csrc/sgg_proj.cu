@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(256) pair_conv1_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) base[j] = bias ? __ldg(bias + ch * 8 + j) : 0.f;
         float sv[8];                                        // bias + the subject's half, kept while the subject stays
-        int64_t cur = -2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sv[j] = base[j];        // (what an out-of-range subject index leaves: -1 is one)
+        int64_t cur = -1;
         const int64_t p_end = min(num_pairs, (run + 1) * kPairRun);
         for (int64_t p = run * kPairRun; p < p_end; ++p) {
             const int64_t a = ixs[p], b = ixo[p];
