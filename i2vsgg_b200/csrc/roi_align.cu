@@ -805,6 +805,17 @@ static LatticeWs carve_lattice_ws(void* ws, int batch, int num_rois, bool lists 
     return w;
 }
 
+// What the last lattice_prep of this host thread left in which workspace: lets the backward of a step take the forward's
+// tables and lists (rois == NULL) and refuse when they are not there.
+struct LastPrep {
+    const void* tab;
+    cudaStream_t stream;
+    int batch, num_rois, H, W, GH, GW;
+    float scale;
+    bool lists;
+};
+static thread_local LastPrep g_last_prep{};
+
 static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W, int GH, int GW, float scale,
                         const LatticeWs& w, bool lists, cudaStream_t stream, float ptab_scale = 0.f,
                         bool backward = false) {
@@ -821,6 +832,7 @@ static int lattice_prep(const float* rois, int batch, int num_rois, int H, int W
         roi_bucket_kernel<<<batch + 1, 256, 0, stream>>>(w.roi_batch, num_rois, batch + 1, w.counts, w.starts, w.order);
         I2V_TRY(check_launch("roi_bucket_kernel"));
     }
+    g_last_prep = LastPrep{w.tab, stream, batch, num_rois, H, W, GH, GW, scale, lists};
     return I2V_OK;
 }
 
@@ -1002,8 +1014,11 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
                                    size_t workspace_bytes, bool zero_first, cudaStream_t stream) {
     LatticeWs w;
     int GH, GW;
-    I2V_TRY(roi_align_check("roi_align_backward", grad_out, rois, grad_in, batch, channels, height, width, num_rois,
-                            pooled_h, pooled_w, pool_mode, impl, GH, GW));
+    // rois == NULL: the workspace still holds the tables and per-frame lists that i2v_roi_align_forward left there for the
+    // same RoIs and geometry (a training step runs the two back to back); only the phased kernel takes them as they are
+    const bool reuse = rois == nullptr && num_rois > 0;
+    I2V_TRY(roi_align_check("roi_align_backward", grad_out, reuse ? grad_out : rois, grad_in, batch, channels, height, width,
+                            num_rois, pooled_h, pooled_w, pool_mode, impl, GH, GW));
     I2V_REQUIRE(pool_mode != I2V_POOL_MAX || features || num_rois == 0, "roi_align_backward: POOL_MAX needs the features");
     size_t in_elems = (size_t)batch * channels * height * width;
     if (in_elems == 0) return I2V_OK;
@@ -1029,9 +1044,23 @@ static int roi_align_backward_impl(const float* grad_out, const float* features,
     }
     // AUTO takes the phased kernel: 1.59 ms on config 2 against 2.28 ms for the warp-per-channel-pair plane kernel and
     // 2.35 ms for the row-owner kernel (profiles/README.md); the other two stay selectable and serve as cross-checks
+    if (reuse && !(can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO))) {
+        set_error("roi_align_backward: rois == NULL (tables of the preceding forward call) needs the phased kernel");
+        return I2V_ERR_UNSUPPORTED;
+    }
     if (can_phase && (impl == I2V_IMPL_PHASE || impl == I2V_IMPL_AUTO)) {
         I2V_TRY(carve_checked("roi_align_backward", workspace, workspace_bytes, batch, num_rois, true, w));
-        I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        if (reuse) {
+            const LastPrep& lp = g_last_prep;
+            if (!(lp.lists && lp.tab == w.tab && lp.stream == stream && lp.batch == batch && lp.num_rois == num_rois &&
+                  lp.H == height && lp.W == width && lp.GH == GH && lp.GW == GW && lp.scale == spatial_scale)) {
+                set_error("roi_align_backward: rois == NULL, but this workspace does not hold the tables of a forward call with "
+                          "the same RoI count, batch, map, pooled size, scale and stream");
+                return I2V_ERR_INVALID;
+            }
+        } else {
+            I2V_TRY(lattice_prep(rois, batch, num_rois, height, width, GH, GW, spatial_scale, w, true, stream));
+        }
         return launch_bwd_phase(grad_out, w.tab, w.ptab, w.order, w.starts, grad_in, batch, channels, height, width,
                                 num_rois, pool_mode, zero_first ? 0 : 1, stream);
     }

@@ -102,6 +102,9 @@ int i2v_roi_align_forward(const float* features, const float* rois, float* out, 
 /* grad_out [N,C,ph,pw] -> grad_in [B,C,H,W], fully OVERWRITTEN (no pre-zeroing needed).
  * Semantics: functions/roi_align.py:37-51 + roi_align_kernel.cu:94-143 behind the pool's backward.
  * `features` is read only for I2V_POOL_MAX (arg-max routing) and may be NULL otherwise. */
+/* `rois` may be NULL when `workspace` still holds what i2v_roi_align_forward left there for the same RoIs, batch, map and
+ * pooled size (plane-resident forward kernels; a training step runs the two calls back to back): the backward then skips
+ * its own table and list kernels.  Phased kernel only (impl AUTO / PHASE where it applies), I2V_ERR_UNSUPPORTED otherwise. */
 int i2v_roi_align_backward(const float* grad_out, const float* features, const float* rois, float* grad_in,
                            int batch, int channels, int height, int width, int num_rois, int pooled_h,
                            int pooled_w, float spatial_scale, int pool_mode, int impl, void* workspace,

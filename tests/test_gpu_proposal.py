@@ -240,6 +240,35 @@ def test_host_pipeline_chunked_copy_equals_device_step():
             assert torch.equal(a, b.cpu())
 
 
+def test_step_backward_on_the_forward_tables_equals_the_plain_call(ops):
+    """`HostPipeline` hands the backward of a step rois = NULL (the forward call left this batch's tables and lists in the
+    workspace): same gradient, bit for bit, as the stand-alone call that builds its own; and the library refuses NULL when
+    the workspace holds no such tables."""
+    import ctypes
+    from i2vsgg_b200 import _lib
+    from i2vsgg_b200.pipeline import HostPipeline
+    frames, ch = 3, 32
+    dev = torch.device("cuda", 0)
+    pipe = HostPipeline(dev, frames, ch, 38, 63, 7, 1 / 16, 3000, 50, 0.7)
+    assert pipe._share_tables
+    cls, reg = synth.rpn_outputs(61, batch=frames)
+    g = torch.Generator().manual_seed(8)
+    feat = torch.randn((frames, ch, 38, 63), generator=g).to(dev)
+    grad = torch.randn((frames * 50, ch, 7, 7), generator=g).to(dev)
+    rois, pooled, grad_in = pipe.device_step(cuda(cls), cuda(reg), cuda(synth.im_info(frames)), feat, grad)
+    torch.cuda.synchronize()
+    want = ops.roi_align_backward(grad, None, rois.reshape(-1, 5), (frames, ch, 38, 63), 7, 7, 1 / 16, "avg")
+    assert torch.equal(grad_in, want)
+    lib = _lib.load()
+    nb = lib.i2v_roi_align_workspace_bytes(frames, frames * 50)
+    fresh = torch.zeros(2 * nb + 512, dtype=torch.uint8, device=dev)[nb + 256:]     # an address no call has prepared
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.i2v_roi_align_backward(p(grad), None, None, p(grad_in), frames, ch, 38, 63, frames * 50, 7, 7, 1 / 16,
+                                    _lib.POOL_AVG, _lib.IMPL_AUTO, p(fresh), fresh.numel(),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc != 0
+
+
 def test_host_pipeline_two_steps_in_flight():
     """`host_step_async` with step i+1 issued before step i is awaited (alternating result slots, shared device buffers)
     returns, for a sequence of DIFFERENT batches, exactly what the device-resident step computes for each."""
