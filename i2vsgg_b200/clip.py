@@ -23,6 +23,7 @@ class ClipRunner:
         self.group, self.top_k = int(frames_per_group), int(top_k)
         self.graphs = bool(graphs)
         self._captured = {}
+        self._side = None
 
     def _group_replayed(self, fmap, boxes, classes, conf):
         """`_group` through a CUDA graph: static input buffers are overwritten, the graph replayed, the outputs copied out."""
@@ -85,17 +86,38 @@ class ClipRunner:
         dev = boxes.device
         anchors = torch.from_numpy(synth.BASE_ANCHORS).to(dev)
         recs, cnts, kept = [], [], []
-        for f0 in range(0, hi - lo, self.group):
+        # Software pipelining over frame groups: the detector side of group g+1 (proposal decode + NMS, RoIAlignAvg) is
+        # issued on a high-priority side stream before the relation stage of group g on the main stream, which waits only
+        # for the detector side of ITS group (in the full model the detector head, out of scope here, sits on that edge).
+        # The proposal chain is latency-bound on a few SMs and slots in under the relation stage's GEMMs.
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev, priority=-1)
+        side = self._side
+        side.wait_stream(main)
+        starts = list(range(0, hi - lo, self.group))
+
+        def detector(f0):
             f1 = min(hi - lo, f0 + self.group)
-            fm = fmaps[f0:f1]
-            rois, nkeep = ops.proposal_forward(rpn_cls[f0:f1], rpn_reg[f0:f1], im_info[f0:f1], anchors, 16, pre_nms,
-                                               post_nms, nms_thresh, return_counts=True)
-            ops.roi_align_forward(fm, rois.reshape(-1, 5), 7, 7, spatial_scale, "avg")
+            with torch.cuda.stream(side):
+                fm = fmaps[f0:f1]
+                rois, nkeep = ops.proposal_forward(rpn_cls[f0:f1], rpn_reg[f0:f1], im_info[f0:f1], anchors, 16, pre_nms,
+                                                   post_nms, nms_thresh, return_counts=True)
+                ops.roi_align_forward(fm, rois.reshape(-1, 5), 7, 7, spatial_scale, "avg")
+                return nkeep, side.record_event()
+
+        pending = detector(starts[0]) if starts else None
+        for gi, f0 in enumerate(starts):
+            f1 = min(hi - lo, f0 + self.group)
+            nkeep, ready = pending
+            pending = detector(starts[gi + 1]) if gi + 1 < len(starts) else None
+            main.wait_event(ready)
             step = self._group_replayed if self.graphs else self._group
-            r, c = step(fm, boxes[f0:f1], classes[f0:f1], conf[f0:f1])
+            r, c = step(fmaps[f0:f1], boxes[f0:f1], classes[f0:f1], conf[f0:f1])
             recs.append(r)
             cnts.append(c)
             kept.append(nkeep)
+        main.wait_stream(side)
         rec = torch.cat(recs) if recs else torch.empty((0, self.top_k, shard.RECORD_WIDTH), device=dev)
         cnt = torch.cat(cnts) if cnts else torch.empty((0,), dtype=torch.int32, device=dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

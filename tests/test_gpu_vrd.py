@@ -302,6 +302,33 @@ def test_clip_runner_groups_frames_without_changing_records(orc):
     assert torch.equal(rec1[2], want) and int(cnt1[2]) == int(wc[0])
 
 
+def test_clip_runner_full_path_pipelines_the_detector_side_without_changing_results(orc):
+    """`run_full` issues the detector side of the next frame group (proposal decode + NMS, RoIAlignAvg) on a side stream
+    under the relation stage of the current one: the records must equal `run`'s and the kept-proposal counts those of a
+    plain proposal call, whatever the group size."""
+    from i2vsgg_b200 import ops
+    from i2vsgg_b200.clip import ClipRunner
+    args = synth.VrdArgs(vrd_in_channels=32, vrd_hidden=256)
+    head = build(args, synth.vrd_params(3, args), synth.prd_vectors(5, args.num_relations))
+    frames, n = 7, 9
+    boxes, classes, conf = synth.clip_detections(8, frames, n)
+    fmaps = torch.from_numpy(synth.feature_map(50, frames, 32)).cuda()
+    b = torch.from_numpy(boxes).cuda()
+    c = torch.from_numpy(np.tile(classes, (frames, 1))).cuda()
+    s = torch.from_numpy(np.tile(conf, (frames, 1))).cuda()
+    cls_h, reg_h = synth.rpn_outputs(70, batch=frames)
+    cls, reg, info = (torch.from_numpy(a).cuda() for a in (cls_h, reg_h, synth.im_info(frames)))
+    want_rec, want_cnt = ClipRunner(head, synth.IM_H, synth.IM_W, 2).run(fmaps, b, c, s, frames)
+    _, want_kept = ops.proposal_forward(cls, reg, info, torch.from_numpy(synth.BASE_ANCHORS).cuda(), 16, 6000, 300, 0.7,
+                                        return_counts=True)
+    for group in (1, 3, 4):
+        rec, cnt, kept = ClipRunner(head, synth.IM_H, synth.IM_W, group).run_full(cls, reg, info, fmaps, b, c, s, frames,
+                                                                                   pre_nms=6000)
+        torch.cuda.synchronize()
+        assert torch.equal(rec, want_rec) and torch.equal(cnt, want_cnt)
+        assert torch.equal(kept.cpu(), want_kept.cpu())
+
+
 @pytest.mark.parametrize("n_det", [1, 2])
 def test_vrd_tiny_frames(orc, n_det):
     """One detection has no pair (the reference's detection_output returns None there, lib/utils.py:585-586); two have
