@@ -40,6 +40,30 @@ def test_association_oracle_equals_reference_live():
     assert assoc._iou([0, 0, 10, 10], [5, 5, 15, 15]) == ref["_iou"]([0, 0, 10, 10], [5, 5, 15, 15])
 
 
+@pytest.mark.needs_reference
+def test_association_oracle_equals_reference_live_on_long_relations():
+    """Relations of several hundred frames (tracks that never miss a frame): their mean confidence, a sort key, is numpy's
+    pairwise summation above 128 terms -- the case the device kernel once got wrong by overrunning its stack."""
+    ref = assoc.reference_functions()
+    rec, cnt = synth.clip_records(seed=21, frames=640, tracks=14, clutter=6, dropout=0.0)
+    fr = synth.records_to_frame_relations(rec, cnt)
+    want = ref["association"]({"v": [[f, list(p)] for f, p in fr]})["v"]
+    got = assoc.association({"v": fr})["v"]
+    assert got == want and max(r["duration"][1] - r["duration"][0] for r in got) > 256
+
+
+def test_conv_layer_takes_parity_planes_only_where_the_kernel_applies():
+    """`Conv2d.takes_split`: stride 2, odd kernel with "same" padding, even map, output positions dividing a 128-row tile."""
+    from i2vsgg_b200.model.faster_rcnn.utils import Conv2d
+    assert Conv2d(96, 128, 5, same_padding=True, stride=2).takes_split(16, 16, 96)       # conv_lo's second layer
+    assert not Conv2d(96, 128, 5, same_padding=True, stride=1).takes_split(16, 16, 96)   # stride 1
+    assert not Conv2d(96, 128, 5, same_padding=False, stride=2).takes_split(16, 16, 96)  # no padding
+    assert not Conv2d(96, 128, 5, same_padding=True, stride=2).takes_split(15, 16, 96)   # odd map
+    assert not Conv2d(96, 128, 5, same_padding=True, stride=2).takes_split(16, 16, 64)   # channel count of another layer
+    assert not Conv2d(96, 256, 5, same_padding=True, stride=2).takes_split(16, 16, 96)   # more than one tile column
+    assert not Conv2d(96, 128, 5, same_padding=True, stride=2).takes_split(20, 20, 96)   # 100 positions do not divide 128
+
+
 def test_fill_empty_frames_rules():
     mk = lambda pattern: [[i, [1] if c == "x" else []] for i, c in enumerate(pattern)]
     assert assoc.fill_empty_frames(mk("x.x")) == [-1, 0, -1]                 # tie: the earlier neighbour
