@@ -24,6 +24,7 @@ class ClipRunner:
         self.graphs = bool(graphs)
         self._captured = {}
         self._side = None
+        self._index = {}
 
     def _group_replayed(self, fmap, boxes, classes, conf):
         """`_group` through a CUDA graph: static input buffers are overwritten, the graph replayed, the outputs copied out."""
@@ -57,15 +58,17 @@ class ClipRunner:
         F, N = boxes.shape[:2]
         dev = fmap.device
         P = N * (N - 1)
-        rep1, inv1 = sgg.unordered_pairs(N, dev)
-        U = rep1.numel()
+        key = (F, N, dev.index)
+        if key not in self._index:      # per group shape: the frame column of the RoIs and the unordered-pair index maps
+            rep1, inv1 = sgg.unordered_pairs(N, dev)
+            offs = torch.arange(F, device=dev)
+            self._index[key] = (torch.arange(F, device=dev, dtype=torch.float32).repeat_interleave(N)[:, None].contiguous(),
+                                (rep1[None, :] + offs[:, None] * P).reshape(-1).contiguous(),
+                                (inv1[None, :] + offs[:, None] * rep1.numel()).reshape(-1).contiguous())
+        frame_col, rep, inv = self._index[key]
         boxes = boxes.contiguous()
         ixs, ixo, rel, obj_masks = ops.pair_build_frames(boxes, self.im_h, self.im_w)
-        rois = torch.cat([torch.arange(F, device=dev, dtype=torch.float32).repeat_interleave(N)[:, None],
-                          boxes.reshape(F * N, 4)], 1)
-        offs = torch.arange(F, device=dev)
-        rep = (rep1[None, :] + offs[:, None] * P).reshape(-1)
-        inv = (inv1[None, :] + offs[:, None] * U).reshape(-1)
+        rois = torch.cat([frame_col, boxes.reshape(F * N, 4)], 1)
         scores, _ = self.head(fmap, rois, rel, None, None, ixs, ixo, return_numpy=False, rel_unique=(rep, inv),
                               obj_masks=obj_masks)
         return ops.triplet_topk_frames(scores, conf, classes, boxes, ixs[:P], ixo[:P], self.top_k)
